@@ -1,0 +1,108 @@
+/*
+ * irn_b200.h -- C ABI of libirn_b200.so: the B200 (sm_100a) implementation of the IRN
+ * pseudo-label hot path (jiwoon-ahn/irn).
+ *
+ * The reference has no FFI of its own (pure Python on torch); its seams are Python names
+ * (SURVEY.md section 8(b)).  Each entry point below names the reference code it replaces
+ * (file:line under the reference tree).  INTEGRATION.md shows the ctypes stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; irn_last_error() (thread-local)
+ *    describes the failure.  -1 = bad argument, -2 = CUDA error, -3 = workspace too small,
+ *    -4 = unsupported configuration.
+ *  - device pointers are BORROWED: the caller (PyTorch in this repo) owns every buffer.  The
+ *    library allocates nothing on the device except inside plan objects (irn_net_*) which
+ *    hold the repacked network weights.
+ *  - all device work is enqueued asynchronously on the caller's stream.
+ *  - no global mutable state except constant tables uploaded once per process per device.
+ *  - tensors are dense row-major; "NCHW"/"NHWC" say which.
+ */
+#ifndef IRN_B200_H
+#define IRN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* irn_stream_t; /* a cudaStream_t / CUstream */
+
+const char* irn_last_error(void);
+int irn_version(void);
+
+/* ------------------------------------------------------------------------------------
+ * R1/R2  PathIndex tables (host, integer, bit-exact).
+ * Replaces misc/indexing.py:6-88 (PathIndex.__init__, get_search_paths_dst,
+ * get_path_indices).
+ *
+ * irn_path_index_shape: n_dst = number of half-plane offsets, n_groups = number of distinct
+ *   path lengths; group_len[g] = path length L, group_paths[g] = paths of that length (both
+ *   arrays sized >= 4*radius).
+ * irn_path_index_fill : search_dst int64 [n_dst,2] (dy,dx); search_paths int64, groups
+ *   concatenated, each [n_paths,L,2]; path_indices int64, groups concatenated, each
+ *   [n_paths,L,n_src]; src_indices int64 [n_src]; dst_indices int64 [n_dst,n_src]; with
+ *   n_src = (Hp-rf)*(Wp-2rf), rf = ceil(radius)-1.  Any output pointer may be NULL.
+ */
+int irn_path_index_shape(int radius, int* n_dst, int* n_groups, int* group_len, int* group_paths);
+int irn_path_index_fill(int radius, int Hp, int Wp, int64_t* search_dst, int64_t* search_paths,
+                        int64_t* path_indices, int64_t* src_indices, int64_t* dst_indices);
+
+/* ------------------------------------------------------------------------------------
+ * R3  edge -> affinity (device).  Replaces misc/indexing.py:91-109 (edge_to_affinity) on
+ * the un-padded grid: aff[k,y,x] = 1 - max(edge over path k from (y,x)), 0 when the
+ * destination leaves the image (the reference pads the edge map with 1.0,
+ * misc/indexing.py:150).  edge fp32 [n_img,h,w]; aff fp32 [n_img,n_dst,h,w].
+ */
+int irn_edge_to_affinity(const float* edge, float* aff, int n_img, int h, int w, int radius,
+                         irn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * R3-R6  random walk.  Replaces misc/indexing.py:141-167 (propagate_to_edge) including
+ * affinity_sparse2dense (:112-129) and to_transition_matrix (:132-139): instead of the
+ * dense (hw)^2 matrix squared exp_times times it applies the 2*n_dst+1 tap stencil
+ * y_j <- (sum_i a_ij^beta y_i)/s_j  n_iter = 2^exp_times times, fp64 state.
+ *
+ *  x    fp32 [total_channels,h,w]   seeds, images back to back
+ *  edge fp32 [n_img,h,w]            sigmoid edge map in (0,1)
+ *  out  fp32 [total_channels,h,w]
+ *  chan_offsets  HOST int32 [n_img+1]: channels of image i are [off[i], off[i+1])
+ *  workspace     device, >= irn_rw_workspace_bytes(...) bytes, 256-byte aligned
+ */
+size_t irn_rw_workspace_bytes(int n_img, int h, int w, int total_channels, int radius);
+int irn_random_walk(const float* x, const float* edge, float* out, int n_img,
+                    const int32_t* chan_offsets, int h, int w, int radius, double beta,
+                    int n_iter, void* workspace, size_t workspace_bytes, irn_stream_t stream);
+
+/* Same, selecting the step kernel: variant 0 = production (TMA-staged register-window kernel,
+ * radius 5), 1 = generic bounds-checked kernel (any radius 2..10; validation / fallback for
+ * radii the reference's hot path never uses). */
+int irn_random_walk_variant(const float* x, const float* edge, float* out, int n_img,
+                            const int32_t* chan_offsets, int h, int w, int radius, double beta,
+                            int n_iter, void* workspace, size_t workspace_bytes, int variant,
+                            irn_stream_t stream);
+
+/* Number of kernels the last API call on this thread launched (bench.py's gpu_launches). */
+int irn_rw_last_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * S1  label map.  Replaces step/make_sem_seg_labels.py:43-49 (and the same tail at
+ * step/make_ins_seg_labels.py:137-143): x4 bilinear (align_corners=False), crop to (H,W),
+ * divide by the global max, prepend a constant background plane, argmax (ties -> lowest
+ * index), map through keys.
+ *
+ *  rw   fp32 [C,h,w] one image;  keys_dev device int32 [C+1] (entry 0 = background id) or
+ *  NULL (identity);  outputs, each optional (NULL): labels uint8 [H,W] = keys[argmax];
+ *  index_out int32 [H,W] = raw argmax (instance path: C may exceed 255);  up_norm fp32
+ *  [C,H,W] = normalised upsampled scores (instance scoring).  scratch: device, >= 16 bytes.
+ */
+int irn_rw_labels(const float* rw, int C, int h, int w, int H, int W, float bg_thres,
+                  const int32_t* keys_dev, uint8_t* labels, int32_t* index_out, float* up_norm,
+                  void* scratch, irn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRN_B200_H */

@@ -1,0 +1,37 @@
+// Shared host-side helpers for libirn_b200.so: error reporting and launch checks.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/irn_b200.h"
+
+namespace irn {
+
+enum { kOk = 0, kBadArg = -1, kCudaError = -2, kWorkspace = -3, kUnsupported = -4 };
+
+char* last_error_buf();             // thread-local, 512 bytes
+int fail(int code, const char* fmt, ...);
+int& launch_counter();              // thread-local count of kernels launched by the last API call
+
+inline int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return kOk;
+    return fail(kCudaError, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define IRN_CUDA(call)                                            \
+    do {                                                          \
+        int _rc = ::irn::check_cuda((call), #call);               \
+        if (_rc != 0) return _rc;                                 \
+    } while (0)
+
+#define IRN_LAUNCH_CHECK(name)                                    \
+    do {                                                          \
+        ::irn::launch_counter()++;                                \
+        int _rc = ::irn::check_cuda(cudaGetLastError(), name);    \
+        if (_rc != 0) return _rc;                                 \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace irn

@@ -1,0 +1,521 @@
+// R3-R6: edge -> affinity -> random walk, as a 69-tap stencil iterated on the device.
+//
+// Reference: misc/indexing.py:91-167.  The reference densifies the affinities to an (hw)^2
+// matrix on the CPU, column-normalises it and squares it exp_times times.  Here the same
+// operator  y_j <- (sum_i a_ij^beta y_i) / s_j ,  s_j = 1 + sum_i a_ij^beta  (A symmetric)
+// is applied n_iter = 2^exp_times times with the 34 half-plane weights per pixel kept in
+// fp32 and the state / accumulator in fp64 (fp32 state misses the 1e-4 bar).
+//
+// HBM layout (workspace), row pitch wp = round_up(w, 4) so every row is 16-byte aligned for TMA:
+//   W[img][34][h][wp] fp32   a^beta per half-plane offset, 0 when the destination leaves the image
+//   inv_s[img][h][wp] fp64   1 / (1 + sum of the 68 incident weights)
+//   y[2][chan][h][wp] fp64   ping-pong walk state
+#include <mutex>
+#include <type_traits>
+
+#include "common.h"
+#include "path_tables.h"
+#include "tma.cuh"
+
+namespace irn {
+
+// ---------------------------------------------------------------- device path tables
+constexpr int kMaxDst = 160;    // radius 10 has 152 destinations
+constexpr int kMaxPts = 2304;
+
+struct DevTables {
+    int n_dst;
+    int radius;
+    short plane[kMaxDst];        // internal W plane of destination k
+    signed char dy[kMaxDst], dx[kMaxDst];
+    short pstart[kMaxDst + 1];
+    signed char py[kMaxPts], px[kMaxPts];
+};
+__constant__ DevTables c_tab;
+
+static std::mutex g_tab_mutex;
+static int g_tab_radius[64] = {0};   // per device: radius currently resident in c_tab
+static int g_tab_ndst[64] = {0};
+
+// Internal plane order for radius 5, grouped by |dx| so the step kernel can stream one |dx| class
+// of planes at a time through shared memory:  class c holds dx=+c (dy = 0..maxdy; dy=0 only exists
+// for dx>0) then dx=-c (dy = 1..maxdy).  Class sizes 4,9,9,7,5 = 34.
+__host__ __device__ constexpr int cls_base5(int c) { return c == 0 ? 0 : c == 1 ? 4 : c == 2 ? 13 : c == 3 ? 22 : c == 4 ? 29 : 34; }
+__host__ __device__ constexpr int cls_maxdy5(int c) { return c <= 2 ? 4 : c == 3 ? 3 : 2; }
+__host__ __device__ constexpr int plane5(int dy, int dx) {
+    const int c = dx < 0 ? -dx : dx;
+    if (c > 4 || dy < 0 || dy > cls_maxdy5(c)) return -1;
+    if (dx == 0) return dy >= 1 ? dy - 1 : -1;
+    if (dx > 0) return cls_base5(c) + dy;
+    return dy >= 1 ? cls_base5(c) + cls_maxdy5(c) + dy : -1;
+}
+static_assert(plane5(1, 0) == 0 && plane5(0, 1) == 4 && plane5(4, 1) == 8 && plane5(1, -1) == 9 && plane5(4, -1) == 12 &&
+                  plane5(0, 2) == 13 && plane5(3, -3) == 28 && plane5(0, 4) == 29 && plane5(2, -4) == 33 && plane5(3, 4) == -1 &&
+                  plane5(4, 3) == -1 && plane5(0, 0) == -1 && plane5(0, -1) == -1,
+              "radius-5 plane order");
+
+static int upload_tables(int radius, cudaStream_t stream, int* n_dst_out) {
+    int dev = 0;
+    IRN_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    if (dev < 64 && g_tab_radius[dev] == radius) {
+        if (n_dst_out) *n_dst_out = g_tab_ndst[dev];
+        return kOk;
+    }
+    PathTable t = build_path_table(radius);
+    if ((int)t.dst.size() > kMaxDst || (int)t.points.size() > kMaxPts)
+        return fail(kUnsupported, "radius %d: %zu destinations / %zu path points exceed the device table", radius,
+                    t.dst.size(), t.points.size());
+    static DevTables h;   // guarded by g_tab_mutex
+    h.n_dst = (int)t.dst.size();
+    h.radius = radius;
+    for (int k = 0; k < h.n_dst; ++k) {
+        const int dy = t.dst[k].first, dx = t.dst[k].second;
+        h.plane[k] = (short)(radius == 5 ? plane5(dy, dx) : k);
+        h.dy[k] = (signed char)dy;
+        h.dx[k] = (signed char)dx;
+        h.pstart[k] = (short)t.path_start[k];
+    }
+    h.pstart[h.n_dst] = (short)t.path_start[h.n_dst];
+    for (size_t j = 0; j < t.points.size(); ++j) {
+        h.py[j] = (signed char)t.points[j].first;
+        h.px[j] = (signed char)t.points[j].second;
+    }
+    IRN_CUDA(cudaMemcpyToSymbolAsync(c_tab, &h, sizeof(h), 0, cudaMemcpyHostToDevice, stream));
+    IRN_CUDA(cudaStreamSynchronize(stream));   // `h` is reused; happens once per (device, radius)
+    if (dev < 64) {
+        g_tab_radius[dev] = radius;
+        g_tab_ndst[dev] = h.n_dst;
+    }
+    if (n_dst_out) *n_dst_out = h.n_dst;
+    return kOk;
+}
+
+// ---------------------------------------------------------------- affinity
+__device__ __forceinline__ double pow_weight(float a, double beta, int ibeta) {
+    double b = (double)a;
+    if (ibeta > 0) {   // exact repeated squaring in fp64, rounded once to fp32 by the caller
+        double r = 1.0;
+        int e = ibeta;
+        while (e) {
+            if (e & 1) r *= b;
+            b *= b;
+            e >>= 1;
+        }
+        return r;
+    }
+    return pow(b, beta);
+}
+
+constexpr int kAffTX = 32, kAffTY = 8;
+
+// MODE 0: write a^beta into the internal plane order, row pitch `pitch` (walk workspace)
+// MODE 1: write a in reference destination order, dense rows (irn_edge_to_affinity)
+template <int MODE>
+__global__ void __launch_bounds__(kAffTX* kAffTY)
+rw_affinity_kernel(const float* __restrict__ edge, float* __restrict__ out, int h, int w, int pitch, double beta, int ibeta) {
+    extern __shared__ float s_edge[];   // [(TY + R) x (TX + 2R)], R = radius - 1
+    const int R = c_tab.radius - 1;
+    const int SW = kAffTX + 2 * R;
+    const int tiles_x = (w + kAffTX - 1) / kAffTX;
+    const int x0 = (blockIdx.x % tiles_x) * kAffTX, y0 = (blockIdx.x / tiles_x) * kAffTY;
+    const int img = blockIdx.y;
+    const float* e = edge + (size_t)img * h * w;
+    const int n = (kAffTY + R) * SW;
+    for (int i = threadIdx.y * kAffTX + threadIdx.x; i < n; i += kAffTX * kAffTY) {
+        const int yy = y0 + i / SW, xx = x0 - R + i % SW;
+        s_edge[i] = (yy < h && xx >= 0 && xx < w) ? e[(size_t)yy * w + xx] : 1.0f;   // pad value 1.0 (misc/indexing.py:150)
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int n_dst = c_tab.n_dst;
+    const size_t plane_sz = (size_t)h * pitch;
+    float* o = out + (size_t)img * n_dst * plane_sz + (size_t)y * pitch + x;
+    for (int k = 0; k < n_dst; ++k) {
+        float m = 0.f;
+        for (int j = c_tab.pstart[k]; j < c_tab.pstart[k + 1]; ++j)
+            m = fmaxf(m, s_edge[(threadIdx.y + c_tab.py[j]) * SW + threadIdx.x + R + c_tab.px[j]]);
+        const float a = 1.0f - m;   // misc/indexing.py:106
+        if (MODE == 0)
+            o[(size_t)c_tab.plane[k] * plane_sz] = (float)pow_weight(a, beta, ibeta);   // misc/indexing.py:133
+        else
+            o[(size_t)k * plane_sz] = a;
+    }
+}
+
+// inv_s[p] = 1 / (1 + sum_k W_k(p) + sum_k W_k(p - d_k))      (misc/indexing.py:124,135)
+__global__ void rw_rowsum_kernel(const float* __restrict__ W, double* __restrict__ inv_s, int h, int w, int pitch) {
+    const int img = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= h * w) return;
+    const int y = p / w, x = p % w;
+    const int n_dst = c_tab.n_dst;
+    const size_t plane_sz = (size_t)h * pitch;
+    const float* Wi = W + (size_t)img * n_dst * plane_sz;
+    double s = 1.0;
+    for (int k = 0; k < n_dst; ++k) {
+        const float* Wk = Wi + (size_t)c_tab.plane[k] * plane_sz;
+        s += (double)Wk[y * pitch + x];
+        const int yy = y - c_tab.dy[k], xx = x - c_tab.dx[k];
+        if (yy >= 0 && xx >= 0 && xx < w) s += (double)Wk[yy * pitch + xx];
+    }
+    inv_s[(size_t)img * plane_sz + (size_t)y * pitch + x] = 1.0 / s;
+}
+
+// y0 = x * (1 - edge) in fp32 (misc/indexing.py:162), widened to fp64
+__global__ void rw_init_kernel(const float* __restrict__ x, const float* __restrict__ edge, double* __restrict__ y,
+                               const int* __restrict__ chan_off, int h, int w, int pitch) {
+    const int img = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int hw = h * w;
+    if (p >= hw) return;
+    const int yy = p / w, xx = p % w;
+    const float om = 1.0f - edge[(size_t)img * hw + p];
+    for (int c = chan_off[img]; c < chan_off[img + 1]; ++c)
+        y[((size_t)c * h + yy) * pitch + xx] = (double)__fmul_rn(x[(size_t)c * hw + p], om);
+}
+
+__global__ void rw_finish_kernel(const double* __restrict__ y, float* __restrict__ out, int totc, int h, int w, int pitch) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)totc * h * w) return;
+    const int xx = (int)(i % w);
+    const size_t row = i / w;   // c*h + y
+    out[i] = (float)y[row * pitch + xx];
+}
+
+// ---------------------------------------------------------------- generic step (any radius; validation / fallback)
+// One thread per pixel, all channels; bounds-checked global loads, tables in constant memory.
+__global__ void rw_step_generic_kernel(const float* __restrict__ W, const double* __restrict__ inv_s,
+                                       const double* __restrict__ yin, double* __restrict__ yout,
+                                       const int* __restrict__ chan_off, int h, int w, int pitch) {
+    const int img = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= h * w) return;
+    const int y = p / w, x = p % w;
+    const int n_dst = c_tab.n_dst;
+    const size_t plane_sz = (size_t)h * pitch;
+    const float* Wi = W + (size_t)img * n_dst * plane_sz;
+    const double is = inv_s[(size_t)img * plane_sz + (size_t)y * pitch + x];
+    for (int c = chan_off[img]; c < chan_off[img + 1]; ++c) {
+        const double* yc = yin + (size_t)c * plane_sz;
+        double acc = yc[y * pitch + x];
+        for (int k = 0; k < n_dst; ++k) {
+            const float* Wk = Wi + (size_t)c_tab.plane[k] * plane_sz;
+            const int dy = c_tab.dy[k], dx = c_tab.dx[k];
+            const int yf = y + dy, xf = x + dx;
+            if (yf < h && xf >= 0 && xf < w) acc = fma((double)Wk[y * pitch + x], yc[yf * pitch + xf], acc);
+            const int yb = y - dy, xb = x - dx;
+            if (yb >= 0 && xb >= 0 && xb < w) acc = fma((double)Wk[yb * pitch + xb], yc[yb * pitch + xb], acc);
+        }
+        yout[(size_t)c * plane_sz + (size_t)y * pitch + x] = acc * is;
+    }
+}
+
+// ---------------------------------------------------------------- TMA step (radius 5)
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
+constexpr int kR = 4;                 // stencil reach for radius 5
+constexpr int kTX = 32;               // tile width = one warp
+constexpr int kPY = 4;                // rows per thread (register window)
+constexpr int kWarps = 4;
+constexpr int kTY = kPY * kWarps;     // 16
+constexpr int kSW = kTX + 2 * kR;     // 40 columns staged (x0-4 .. x0+35)
+constexpr int kYH = kTY + 2 * kR;     // 24 state rows staged (y0-4 .. y0+19)
+constexpr int kWH = kTY + kR;         // 20 weight rows staged (y0-4 .. y0+15): mirrored taps only look up / left
+constexpr int kMaxClsPlanes = 9;
+constexpr int kMaxCH = 4;
+constexpr int kWBufFloats = kMaxClsPlanes * kWH * kSW;   // 7200 floats = 28.8 KB per buffer
+
+constexpr size_t rw_tma_smem_bytes(int ch) {
+    return 128 /*alignment slack*/ + (size_t)ch * kYH * kSW * sizeof(double) + 2 * (size_t)kWBufFloats * sizeof(float) + 64;
+}
+
+struct RwMaps {
+    CUtensorMap w[5];   // weights, one map per |dx| class (box depth = class size)
+    CUtensorMap y;      // state being read
+};
+
+// One walk step for CH channels of one 32x16 tile.  Thread = one column, kPY consecutive rows.
+// For every column offset dxc and window row r the state value y(yb+r, x+dxc) is read from shared
+// memory ONCE and used by every (row j, tap) pair it participates in:
+//   forward tap  d=(r-j, dxc):   weight W_d(p_j)                      (own cell of plane d)
+//   mirrored tap d=(j-r,-dxc):   weight W_d(p_j - d) = W_d at the very cell being read
+// The 34 weight planes stream through two shared-memory buffers one |dx| class at a time (TMA,
+// zero-filled outside the image, which is exactly the reference's "affinity 0 to anything outside").
+template <int CH>
+__global__ void __launch_bounds__(kTX* kWarps)
+rw_step_tma_kernel(const __grid_constant__ RwMaps maps, const double* __restrict__ inv_s, double* __restrict__ yout,
+                   const int* __restrict__ chan_off, int h, int w, int pitch) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];   // TMA destinations need 128-byte alignment
+    double* s_y = (double*)smem_raw;                                              // [CH][kYH][kSW]
+    float* s_w = (float*)(smem_raw + (size_t)CH * kYH * kSW * sizeof(double));   // [2][<=9][kWH][kSW]
+    uint64_t* bars = (uint64_t*)(s_w + 2 * kWBufFloats);                     // [0]=y, [1],[2]=weight buffers
+
+    const int tid = threadIdx.x;
+    const int tiles_x = (w + kTX - 1) / kTX;
+    const int x0 = (blockIdx.x % tiles_x) * kTX, y0 = (blockIdx.x / tiles_x) * kTY;
+    const int img = blockIdx.y;
+    const int c_begin = chan_off[img], c_end = chan_off[img + 1];
+    if (c_begin >= c_end) return;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int x = x0 + lane;
+    const int ty0 = warp * kPY;
+    const int yb = y0 + ty0;
+    const size_t plane_sz = (size_t)h * pitch;
+    uint32_t ph_y = 0, ph_w0 = 0, ph_w1 = 0;
+
+    for (int c0 = c_begin; c0 < c_end; c0 += CH) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bars[0], (uint32_t)(CH * kYH * kSW * sizeof(double)));
+            tma_load_3d(s_y, &maps.y, &bars[0], x0 - kR, y0 - kR, c0);
+            mbar_arrive_expect_tx(&bars[1], (uint32_t)((cls_base5(1) - cls_base5(0)) * kWH * kSW * sizeof(float)));
+            tma_load_3d(s_w, &maps.w[0], &bars[1], x0 - kR, y0 - kR, img * 34 + cls_base5(0));
+            mbar_arrive_expect_tx(&bars[2], (uint32_t)((cls_base5(2) - cls_base5(1)) * kWH * kSW * sizeof(float)));
+            tma_load_3d(s_w + kWBufFloats, &maps.w[1], &bars[2], x0 - kR, y0 - kR, img * 34 + cls_base5(1));
+        }
+        mbar_wait(&bars[0], ph_y);
+        ph_y ^= 1;
+
+        double acc[kPY][CH];
+#pragma unroll
+        for (int j = 0; j < kPY; ++j)
+#pragma unroll
+            for (int c = 0; c < CH; ++c) acc[j][c] = s_y[(c * kYH + ty0 + j + kR) * kSW + lane + kR];   // diagonal weight 1
+
+        static_for<0, 5>([&](auto CLS) {
+            constexpr int cls = decltype(CLS)::value;
+            constexpr int buf = cls & 1;
+            const float* wb = s_w + buf * kWBufFloats;
+            if constexpr (buf == 0) {
+                mbar_wait(&bars[1], ph_w0);
+                ph_w0 ^= 1;
+            } else {
+                mbar_wait(&bars[2], ph_w1);
+                ph_w1 ^= 1;
+            }
+            static_for<0, (cls == 0 ? 1 : 2)>([&](auto SGN) {
+                constexpr int dxc = decltype(SGN)::value == 0 ? cls : -cls;
+                static_for<-kR, kPY + kR>([&](auto RR) {
+                    constexpr int r = decltype(RR)::value;
+                    double v[CH];
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) v[c] = s_y[(c * kYH + ty0 + r + kR) * kSW + lane + dxc + kR];
+                    static_for<0, kPY>([&](auto JJ) {
+                        constexpr int j = decltype(JJ)::value;
+                        constexpr int dy = r - j;
+                        constexpr int kf = plane5(dy, dxc);
+                        constexpr int kb = plane5(-dy, -dxc);
+                        if constexpr (kf >= 0) {
+                            const double wv = (double)wb[((kf - cls_base5(cls)) * kWH + ty0 + j + kR) * kSW + lane + kR];
+#pragma unroll
+                            for (int c = 0; c < CH; ++c) acc[j][c] = fma(wv, v[c], acc[j][c]);
+                        } else if constexpr (kb >= 0) {
+                            const double wv = (double)wb[((kb - cls_base5(cls)) * kWH + ty0 + r + kR) * kSW + lane + dxc + kR];
+#pragma unroll
+                            for (int c = 0; c < CH; ++c) acc[j][c] = fma(wv, v[c], acc[j][c]);
+                        }
+                    });
+                });
+            });
+            if constexpr (cls + 2 <= 4) {
+                __syncthreads();   // every thread is done reading buffer `buf`
+                if (tid == 0) {
+                    uint64_t* bar = &bars[1 + buf];
+                    mbar_arrive_expect_tx(bar, (uint32_t)((cls_base5(cls + 3) - cls_base5(cls + 2)) * kWH * kSW * sizeof(float)));
+                    tma_load_3d(s_w + buf * kWBufFloats, &maps.w[cls + 2], bar, x0 - kR, y0 - kR, img * 34 + cls_base5(cls + 2));
+                }
+            }
+        });
+
+        if (x < w) {
+#pragma unroll
+            for (int j = 0; j < kPY; ++j) {
+                if (yb + j < h) {
+                    const double is = inv_s[(size_t)img * plane_sz + (size_t)(yb + j) * pitch + x];
+#pragma unroll
+                    for (int c = 0; c < CH; ++c)
+                        if (c0 + c < c_end) yout[(size_t)(c0 + c) * plane_sz + (size_t)(yb + j) * pitch + x] = acc[j][c] * is;
+                }
+            }
+        }
+        __syncthreads();   // s_y / weight buffers are reused by the next channel chunk
+    }
+}
+
+// ---------------------------------------------------------------- workspace carving
+struct RwWorkspace {
+    float* W;
+    double* inv_s;
+    double* y[2];
+    int* chan_off;
+    int pitch;
+    size_t bytes;
+};
+
+static RwWorkspace carve(void* base, int n_img, int h, int w, int totc, int n_dst) {
+    RwWorkspace ws;
+    ws.pitch = (w + 3) / 4 * 4;
+    const size_t plane_sz = (size_t)h * ws.pitch;
+    char* p = (char*)base;
+    size_t off = 0;
+    ws.W = (float*)(p + off);
+    off += align_up((size_t)n_img * n_dst * plane_sz * sizeof(float), 256);
+    ws.inv_s = (double*)(p + off);
+    off += align_up((size_t)n_img * plane_sz * sizeof(double), 256);
+    for (int i = 0; i < 2; ++i) {
+        ws.y[i] = (double*)(p + off);
+        off += align_up((size_t)totc * plane_sz * sizeof(double), 256);
+    }
+    ws.chan_off = (int*)(p + off);
+    off += align_up((size_t)(n_img + 1) * sizeof(int), 256);
+    ws.bytes = off;
+    return ws;
+}
+
+template <int CH>
+static int launch_tma_steps(const RwWorkspace& ws, int n_img, int totc, int h, int w, int n_iter, cudaStream_t stream) {
+    const int pitch = ws.pitch;
+    RwMaps maps[2];
+    for (int b = 0; b < 2; ++b) {
+        for (int c = 0; c < 5; ++c) {
+            const uint64_t dims[3] = {(uint64_t)w, (uint64_t)h, (uint64_t)n_img * 34};
+            const uint64_t strides[2] = {(uint64_t)pitch * sizeof(float), (uint64_t)pitch * h * sizeof(float)};
+            const uint32_t box[3] = {(uint32_t)kSW, (uint32_t)kWH, (uint32_t)(cls_base5(c + 1) - cls_base5(c))};
+            int rc = make_tensor_map(&maps[b].w[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ws.W, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc) return rc;
+        }
+        const uint64_t dims[3] = {(uint64_t)w, (uint64_t)h, (uint64_t)totc};
+        const uint64_t strides[2] = {(uint64_t)pitch * sizeof(double), (uint64_t)pitch * h * sizeof(double)};
+        const uint32_t box[3] = {(uint32_t)kSW, (uint32_t)kYH, (uint32_t)CH};
+        int rc = make_tensor_map(&maps[b].y, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ws.y[b], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc) return rc;
+    }
+    const size_t smem = rw_tma_smem_bytes(CH);
+    IRN_CUDA(cudaFuncSetAttribute(rw_step_tma_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(((w + kTX - 1) / kTX) * ((h + kTY - 1) / kTY), n_img);
+    for (int it = 0; it < n_iter; ++it) {
+        rw_step_tma_kernel<CH><<<grid, kTX * kWarps, smem, stream>>>(maps[it & 1], ws.inv_s, ws.y[(it + 1) & 1], ws.chan_off, h, w, pitch);
+        IRN_LAUNCH_CHECK("rw_step_tma_kernel");
+    }
+    return kOk;
+}
+
+static int walk_impl(const float* x, const float* edge, float* out, int n_img, const int32_t* chan_offsets, int h, int w,
+                     int radius, double beta, int n_iter, void* workspace, size_t workspace_bytes, int variant,
+                     cudaStream_t stream) {
+    launch_counter() = 0;
+    if (!x || !edge || !out || !chan_offsets || !workspace) return fail(kBadArg, "irn_random_walk: null pointer");
+    if (n_img <= 0 || h <= 0 || w <= 0 || n_iter < 0)
+        return fail(kBadArg, "irn_random_walk: bad size (n_img=%d h=%d w=%d n_iter=%d)", n_img, h, w, n_iter);
+    if (radius < 2 || radius > 10) return fail(kUnsupported, "irn_random_walk: radius %d outside [2,10]", radius);
+    if (chan_offsets[0] != 0) return fail(kBadArg, "irn_random_walk: chan_offsets[0] must be 0");
+    int max_c = 0;
+    for (int i = 0; i < n_img; ++i) {
+        if (chan_offsets[i + 1] < chan_offsets[i]) return fail(kBadArg, "irn_random_walk: chan_offsets not monotone at %d", i);
+        max_c = chan_offsets[i + 1] - chan_offsets[i] > max_c ? chan_offsets[i + 1] - chan_offsets[i] : max_c;
+    }
+    const int totc = chan_offsets[n_img];
+    if (totc == 0) return kOk;
+    if (((uintptr_t)workspace & 255) != 0) return fail(kBadArg, "irn_random_walk: workspace must be 256-byte aligned");
+    int n_dst = 0;
+    int rc = upload_tables(radius, stream, &n_dst);
+    if (rc) return rc;
+    RwWorkspace ws = carve(workspace, n_img, h, w, totc, n_dst);
+    if (ws.bytes > workspace_bytes) return fail(kWorkspace, "irn_random_walk: workspace %zu < required %zu bytes", workspace_bytes, ws.bytes);
+    if ((size_t)n_img * n_dst >= (1u << 30) || (size_t)h * ws.pitch >= (1u << 30)) return fail(kUnsupported, "irn_random_walk: problem too large");
+
+    const int pitch = ws.pitch;
+    const size_t hw = (size_t)h * w;
+    IRN_CUDA(cudaMemcpyAsync(ws.chan_off, chan_offsets, (size_t)(n_img + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    const double rb = nearbyint(beta);
+    const int ibeta = (rb == beta && beta >= 1 && beta <= 64) ? (int)rb : 0;
+    {
+        const int R = radius - 1;
+        dim3 grid(((w + kAffTX - 1) / kAffTX) * ((h + kAffTY - 1) / kAffTY), n_img), block(kAffTX, kAffTY);
+        const size_t smem = (size_t)(kAffTY + R) * (kAffTX + 2 * R) * sizeof(float);
+        rw_affinity_kernel<0><<<grid, block, smem, stream>>>(edge, ws.W, h, w, pitch, beta, ibeta);
+        IRN_LAUNCH_CHECK("rw_affinity_kernel<0>");
+    }
+    dim3 pgrid((unsigned)((hw + 255) / 256), n_img);
+    rw_rowsum_kernel<<<pgrid, 256, 0, stream>>>(ws.W, ws.inv_s, h, w, pitch);
+    IRN_LAUNCH_CHECK("rw_rowsum_kernel");
+    rw_init_kernel<<<pgrid, 256, 0, stream>>>(x, edge, ws.y[0], ws.chan_off, h, w, pitch);
+    IRN_LAUNCH_CHECK("rw_init_kernel");
+
+    if (radius == 5 && variant != 1) {
+        const int ch = max_c >= 4 ? 4 : max_c;
+        if (ch == 1) rc = launch_tma_steps<1>(ws, n_img, totc, h, w, n_iter, stream);
+        else if (ch == 2) rc = launch_tma_steps<2>(ws, n_img, totc, h, w, n_iter, stream);
+        else if (ch == 3) rc = launch_tma_steps<3>(ws, n_img, totc, h, w, n_iter, stream);
+        else rc = launch_tma_steps<4>(ws, n_img, totc, h, w, n_iter, stream);
+        if (rc) return rc;
+    } else {
+        for (int it = 0; it < n_iter; ++it) {
+            rw_step_generic_kernel<<<pgrid, 256, 0, stream>>>(ws.W, ws.inv_s, ws.y[it & 1], ws.y[(it + 1) & 1], ws.chan_off, h, w, pitch);
+            IRN_LAUNCH_CHECK("rw_step_generic_kernel");
+        }
+    }
+    {
+        const size_t n = (size_t)totc * hw;
+        rw_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(ws.y[n_iter & 1], out, totc, h, w, pitch);
+        IRN_LAUNCH_CHECK("rw_finish_kernel");
+    }
+    return kOk;
+}
+
+}  // namespace irn
+
+using namespace irn;
+
+extern "C" int irn_edge_to_affinity(const float* edge, float* aff, int n_img, int h, int w, int radius,
+                                    irn_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    launch_counter() = 0;
+    if (!edge || !aff || n_img <= 0 || h <= 0 || w <= 0) return fail(kBadArg, "irn_edge_to_affinity: bad argument");
+    if (radius < 2 || radius > 10) return fail(kUnsupported, "irn_edge_to_affinity: radius %d outside [2,10]", radius);
+    int rc = upload_tables(radius, stream, nullptr);
+    if (rc) return rc;
+    const int R = radius - 1;
+    dim3 grid(((w + kAffTX - 1) / kAffTX) * ((h + kAffTY - 1) / kAffTY), n_img), block(kAffTX, kAffTY);
+    const size_t smem = (size_t)(kAffTY + R) * (kAffTX + 2 * R) * sizeof(float);
+    rw_affinity_kernel<1><<<grid, block, smem, stream>>>(edge, aff, h, w, w, 1.0, 1);
+    IRN_LAUNCH_CHECK("rw_affinity_kernel<1>");
+    return kOk;
+}
+
+extern "C" size_t irn_rw_workspace_bytes(int n_img, int h, int w, int total_channels, int radius) {
+    if (n_img <= 0 || h <= 0 || w <= 0 || total_channels < 0 || radius < 2 || radius > 10) return 0;
+    const int n_dst = radius == 5 ? 34 : (int)build_path_table(radius).dst.size();
+    return carve(nullptr, n_img, h, w, total_channels, n_dst).bytes;
+}
+
+extern "C" int irn_rw_last_launch_count(void) { return launch_counter(); }
+
+extern "C" int irn_random_walk(const float* x, const float* edge, float* out, int n_img, const int32_t* chan_offsets,
+                               int h, int w, int radius, double beta, int n_iter, void* workspace,
+                               size_t workspace_bytes, irn_stream_t stream) {
+    return walk_impl(x, edge, out, n_img, chan_offsets, h, w, radius, beta, n_iter, workspace, workspace_bytes, 0, (cudaStream_t)stream);
+}
+
+// variant: 0 = production path (TMA step kernel for radius 5), 1 = generic bounds-checked kernel (validation)
+extern "C" int irn_random_walk_variant(const float* x, const float* edge, float* out, int n_img, const int32_t* chan_offsets,
+                                       int h, int w, int radius, double beta, int n_iter, void* workspace,
+                                       size_t workspace_bytes, int variant, irn_stream_t stream) {
+    return walk_impl(x, edge, out, n_img, chan_offsets, h, w, radius, beta, n_iter, workspace, workspace_bytes, variant, (cudaStream_t)stream);
+}

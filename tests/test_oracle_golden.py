@@ -1,0 +1,137 @@
+"""The CPU oracle against the fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import glob
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_path
+from oracle import indexing as oi
+from oracle import nets, steps
+from irn_b200 import synth
+
+
+def _sha(pi):
+    h = hashlib.sha256()
+    for p in pi.path_indices:
+        h.update(np.ascontiguousarray(p, dtype=np.int64).tobytes())
+    h.update(np.ascontiguousarray(pi.src_indices, dtype=np.int64).tobytes())
+    h.update(np.ascontiguousarray(pi.dst_indices, dtype=np.int64).tobytes())
+    h.update(np.ascontiguousarray(pi.search_dst, dtype=np.int64).tobytes())
+    return h.hexdigest()
+
+
+PI = json.load(open(golden_path("path_index.json")))
+
+
+@pytest.mark.parametrize("key", sorted(PI))
+def test_path_index_bit_exact(key):
+    g = PI[key]
+    pi = oi.PathIndex(g["radius"], tuple(g["size"]))
+    assert [list(p.shape) for p in pi.path_indices] == g["group_shapes"]
+    assert np.asarray(pi.search_dst).tolist() == g["search_dst"]
+    assert _sha(pi) == g["sha256"]
+
+
+def test_path_index_survey_known_answer():
+    # sha256 of PathIndex(5, (133,138)) measured on the reference
+    assert PI["r5_133x138"]["sha256"] == "9d6c7172b84f0f3fa9a97ecb3523c2f385ff606614983e632b666704cb2f6042"
+    assert PI["r5_133x138"]["src_head"] == [4, 5, 6, 7, 8]
+
+
+def test_edge_to_affinity_matches_reference():
+    g = np.load(golden_path("affinity_12x17.npz"))
+    edge, aff = g["edge"], g["aff"][0]
+    h, w, r = 12, 17, 5
+    pi = oi.PathIndex(r, (h + r, w + 2 * r))
+    ep = np.ones((h + r, w + 2 * r), np.float32)
+    ep[:h, r:r + w] = edge[0]
+    mine = oi.edge_to_affinity(ep, pi.path_indices)
+    assert np.array_equal(mine, aff)
+    # and the stencil form on the un-padded grid: window = rows 0..h, cols -1..w -> interior [0:h, 1:w+1]
+    W, offs = oi.stencil_weights(edge, 5, beta=1)
+    win = aff.reshape(34, h + 1, w + 2)[:, :h, 1:w + 1]
+    assert np.array_equal(W, win)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(golden_path("rw_*.npz"))), ids=os.path.basename)
+def test_random_walk_oracle(path):
+    g = np.load(path)
+    h, w = g["x"].shape[-2:]
+    n_iter = 2 ** int(g["exp_times"])
+    if h * w <= 48 * 48:   # the faithful dense restatement (O((hw)^2) memory)
+        dense = oi.propagate_to_edge(g["x"], g["edge"], 5, 10, int(g["exp_times"]))
+        assert np.abs(dense - g["rw"]).max() < 2e-6
+    st = oi.propagate_stencil(g["x"], g["edge"], 5, 10, n_iter)
+    # the reference's own fp32 squaring error against the exact operator: SURVEY.md App. B (< 1e-4)
+    assert np.abs(st - g["rw"]).max() < 1e-4
+
+
+def test_cam_forward_oracle():
+    g = np.load(golden_path("cam_forward.npz"))
+    sd = synth.cam_state_dict()
+    with torch.no_grad():
+        for i in range(3):
+            y = nets.cam_forward(torch.from_numpy(g["x%d" % i]), sd).numpy()
+            assert y.shape == g["y%d" % i].shape
+            assert np.abs(y - g["y%d" % i]).max() < 1e-5
+
+
+def test_edge_displacement_oracle():
+    g = np.load(golden_path("irn_forward.npz"))
+    sd = synth.irn_state_dict()
+    with torch.no_grad():
+        for i in range(2):
+            e, d = nets.edge_displacement(torch.from_numpy(g["x%d" % i]), sd)
+            assert np.abs(e.numpy() - g["edge%d" % i]).max() < 1e-5
+            assert np.abs(d.numpy() - g["dp%d" % i]).max() < 1e-4
+
+
+def test_instance_functions_oracle():
+    g = np.load(golden_path("instance_fns.npz"))
+    for i in range(3):
+        dp = g["dp%d" % i]
+        cen = steps.find_centroids(dp)
+        assert np.array_equal(cen, g["centroids%d" % i])
+        shape = tuple(g["instances_shape%d" % i])
+        inst = np.unpackbits(g["instances%d" % i], axis=-1, count=shape[-1]).astype(bool).reshape(shape)
+        assert np.array_equal(steps.cluster_centroids(cen, dp), inst)
+
+
+def test_step_bodies_oracle():
+    """cam_merge / sem_seg_labels restatements against the reference's own _work loops."""
+    from PIL import Image
+    g = np.load(golden_path("steps.npz"))
+    cam_sd, irn_sd = synth.cam_state_dict(), synth.irn_state_dict()
+    for i in range(len(g["ids"])):
+        img = g["img%d" % i]
+        H, W = img.shape[:2]
+        outs = []
+        with torch.no_grad():
+            for s in (1.0, 0.5, 1.5, 2.0):   # step/make_cam.py + voc12/dataloader.py:185-205
+                if s == 1.0:
+                    im = img
+                else:
+                    im = np.asarray(Image.fromarray(img).resize((int(np.round(W * s)), int(np.round(H * s))), Image.BICUBIC))
+                x = synth.normalize_image(im)
+                outs.append(nets.cam_forward(torch.from_numpy(np.stack([x, x[..., ::-1].copy()])), cam_sd))
+            keys, low, high = steps.cam_merge(outs, (H, W), torch.from_numpy(g["label%d" % i]))
+            assert np.array_equal(keys.numpy(), g["cam_keys%d" % i])
+            assert np.abs(low.numpy() - g["cam_cam%d" % i]).max() < 1e-5
+            assert np.abs(high.numpy() - g["cam_high%d" % i]).max() < 1e-5
+            x = synth.normalize_image(img)
+            edge, dp = nets.edge_displacement(torch.from_numpy(np.stack([x, x[..., ::-1].copy()])), irn_sd)
+            rw = oi.propagate_stencil(g["cam_cam%d" % i], edge.numpy(), 5, 10, 256)
+            lab = steps.sem_seg_labels(torch.from_numpy(rw.astype(np.float32)), g["cam_keys%d" % i], (H, W))
+        ref = g["sem%d" % i]
+        assert lab.shape == ref.shape
+        assert (lab != ref).mean() < 2e-3   # pixels on a decision boundary may flip (float walk differs at 1e-5)
+
+
+def test_split_indices():
+    parts = steps.split_indices(10, 3)
+    assert [p.tolist() for p in parts] == [[0, 3, 6, 9], [1, 4, 7], [2, 5, 8]]
