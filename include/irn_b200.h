@@ -102,6 +102,41 @@ int irn_rw_labels(const float* rw, int C, int h, int w, int H, int W, float bg_t
                   const int32_t* keys_dev, uint8_t* labels, int32_t* index_out, float* up_norm,
                   void* scratch, irn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * C2/C3  ResNet-50 trunk + CAM head;  I1/I2  IRNet edge / displacement heads.
+ * Replace net/resnet50.py:17-91, net/resnet50_cam.py:55-70 (CAM.forward) and
+ * net/resnet50_irn.py:23-133,216-234 (Net.forward, MeanShift, EdgeDisplacement.forward).
+ *
+ * A plan (irn_net) owns the repacked weights on the current device.  `params` is a HOST fp32
+ * blob holding the reference checkpoint's tensors in execution order (irn_b200/_pack.py):
+ *   trunk: conv1.weight, bn1.{weight,bias,running_mean,running_var}; then per bottleneck
+ *          conv1,bn1,conv2,bn2,conv3,bn3[,downsample.0,downsample.1] (weights OIHW);
+ *   CAM  : + classifier.weight [20,2048];
+ *   IRN  : + fc_edge1..5 {conv.weight, gn.weight, gn.bias}, fc_edge6.{weight,bias},
+ *          fc_dp1..7 {conv.weight, gn.weight, gn.bias}, fc_dp7.3.weight, mean_shift.running_mean.
+ * FixedBatchNorm (eps 1e-5, inference statistics) is folded into the conv at creation.
+ */
+typedef struct irn_net irn_net;
+int irn_cam_net_create(const float* params, size_t n_floats, irn_net** out);
+int irn_irn_net_create(const float* params, size_t n_floats, irn_net** out);
+void irn_net_destroy(irn_net* net);
+
+/* CAM.forward over B/2 (image, horizontally flipped image) pairs.
+ *   x_nchw fp32 [B,3,H,W] (device), B even -> cam fp32 [B/2,20,ceil(H/16),ceil(W/16)]:
+ *   relu(classifier(trunk(x)))[2p] + relu(...)[2p+1].flip(-1)   (net/resnet50_cam.py:65-68) */
+size_t irn_cam_workspace_bytes(int B, int H, int W);
+int irn_cam_forward(const irn_net* net, const float* x_nchw, int B, int H, int W, float* cam_out,
+                    void* workspace, size_t workspace_bytes, irn_stream_t stream);
+
+/* EdgeDisplacement.forward for one (image, flipped image) pair.
+ *   x_nchw fp32 [2,3,H,W]; zero-padded to crop_size (net/resnet50_irn.py:226) ->
+ *   edge fp32 [1,fh,fw] = sigmoid(e[0]/2 + e[1].flip(-1)/2), dp fp32 [2,fh,fw] = dp[0] - running_mean;
+ *   fh = ceil(H/4), fw = ceil(W/4). */
+size_t irn_edge_displacement_workspace_bytes(int H, int W, int crop_size);
+int irn_edge_displacement_forward(const irn_net* net, const float* x_nchw, int H, int W,
+                                  int crop_size, float* edge_out, float* dp_out, void* workspace,
+                                  size_t workspace_bytes, irn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,14 @@ SIGNATURES = {
     "irn_random_walk_variant": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_double,
                                         c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "irn_rw_last_launch_count": (c_int, []),
+    "irn_cam_net_create": (c_int, [c_void_p, c_size_t, ctypes.POINTER(c_void_p)]),
+    "irn_irn_net_create": (c_int, [c_void_p, c_size_t, ctypes.POINTER(c_void_p)]),
+    "irn_net_destroy": (None, [c_void_p]),
+    "irn_cam_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "irn_cam_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "irn_edge_displacement_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "irn_edge_displacement_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                              c_size_t, c_void_p]),
     "irn_rw_labels": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p]),
 }

@@ -1,0 +1,330 @@
+// SIMT fp32 implicit-GEMM convolution (NHWC) and the small glue kernels of the network path.
+// This is the exact-fp32 path: every conv the tcgen05 kernel (conv_tc.cu) does not cover runs
+// here, and it is the on-device cross-check for the tensor-core path.
+//
+// Reference semantics restated: cross-correlation, zero padding, no bias;
+// FixedBatchNorm (net/resnet50.py:11-14) is folded into (weights, bias) at plan creation.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace irn {
+
+struct ConvGeom {
+    int B, H, W, Cin;        // input NHWC
+    int Ho, Wo, Cout;        // output NHWC
+    int k, stride, pad;
+};
+
+constexpr int kBM = 128, kBN = 64, kBK = 16;
+
+// out[m][n] = act( sum_k A[m][k] * Wt[k][n] + bias[n] + residual[m][n] ),  m = (b,oy,ox), k = (r,s,c)
+// Wt: [k*k*Cin][Cout] row-major.  VEC: Cin % 16 == 0 (a 16-wide k slice never straddles a filter tap).
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(const float* __restrict__ in, const float* __restrict__ wt, const float* __restrict__ bias,
+                 const float* __restrict__ residual, float* __restrict__ out, ConvGeom g, int relu) {
+    __shared__ __align__(16) float As[kBK][kBM + 4];
+    __shared__ __align__(16) float Bs[kBK][kBN];
+    const int tid = threadIdx.x;
+    const int M = g.B * g.Ho * g.Wo;
+    const int K = g.k * g.k * g.Cin;
+    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
+
+    // A-load role: thread loads 8 consecutive k for one row
+    const int a_row = tid >> 1, a_k0 = (tid & 1) * 8;
+    const int am = m0 + a_row;
+    int ab = 0, aoy = 0, aox = 0;
+    const bool a_valid = am < M;
+    if (a_valid) {
+        ab = am / (g.Ho * g.Wo);
+        const int rem = am % (g.Ho * g.Wo);
+        aoy = rem / g.Wo;
+        aox = rem % g.Wo;
+    }
+    // B-load role: thread loads 4 consecutive n for one k
+    const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+
+    // compute role: 8 rows x 4 cols
+    const int tm = (tid >> 4) * 8, tn = (tid & 15) * 4;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += kBK) {
+        // ---- A tile
+        float av[8];
+        if (VEC) {
+            const int kk = k0 + a_k0;            // whole 8-slice lies in one tap
+            const int tap = kk / g.Cin, c = kk % g.Cin;
+            const int r = tap / g.k, s = tap % g.k;
+            const int iy = aoy * g.stride - g.pad + r, ix = aox * g.stride - g.pad + s;
+            if (a_valid && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) {
+                const float4* p = reinterpret_cast<const float4*>(in + (((size_t)ab * g.H + iy) * g.W + ix) * g.Cin + c);
+                const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
+                av[0] = v0.x; av[1] = v0.y; av[2] = v0.z; av[3] = v0.w;
+                av[4] = v1.x; av[5] = v1.y; av[6] = v1.z; av[7] = v1.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) av[i] = 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int kk = k0 + a_k0 + i;
+                float v = 0.f;
+                if (a_valid && kk < K) {
+                    const int tap = kk / g.Cin, c = kk % g.Cin;
+                    const int r = tap / g.k, s = tap % g.k;
+                    const int iy = aoy * g.stride - g.pad + r, ix = aox * g.stride - g.pad + s;
+                    if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) v = __ldg(in + (((size_t)ab * g.H + iy) * g.W + ix) * g.Cin + c);
+                }
+                av[i] = v;
+            }
+        }
+        // ---- B tile
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+            const int kk = k0 + b_k, n = n0 + b_n;
+            if (kk < K) {
+                if (n + 3 < g.Cout && (g.Cout & 3) == 0) {
+                    bv = __ldg(reinterpret_cast<const float4*>(wt + (size_t)kk * g.Cout + n));
+                } else {
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int j = 0; j < 4; ++j)
+                        if (n + j < g.Cout) t[j] = __ldg(wt + (size_t)kk * g.Cout + n + j);
+                    bv = make_float4(t[0], t[1], t[2], t[3]);
+                }
+            }
+        }
+        __syncthreads();   // previous tile fully consumed
+#pragma unroll
+        for (int i = 0; i < 8; ++i) As[a_k0 + i][a_row] = av[i];
+        *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = bv;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kBK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][tm]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][tm + 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tn]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+    }
+    // ---- epilogue
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + tm + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tn + j;
+            if (n >= g.Cout) continue;
+            float v = acc[i][j];
+            if (bias) v += bias[n];
+            if (residual) v += residual[(size_t)m * g.Cout + n];
+            if (relu) v = fmaxf(v, 0.f);
+            out[(size_t)m * g.Cout + n] = v;
+        }
+    }
+}
+
+// NCHW fp32 -> NHWC fp32, optionally zero-padding to (Hp, Wp) on the right/bottom
+// (EdgeDisplacement pads its input to crop_size, net/resnet50_irn.py:226).
+__global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int H, int W,
+                                        int Hp, int Wp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)B * Hp * Wp * C;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int x = (int)(r % Wp);
+    r /= Wp;
+    const int y = (int)(r % Hp);
+    const int b = (int)(r / Hp);
+    out[i] = (y < H && x < W) ? in[(((size_t)b * C + c) * H + y) * W + x] : 0.f;
+}
+
+// MaxPool2d(3, stride 2, pad 1), -inf padding (net/resnet50.py:66).  NHWC, C % 4 == 0.
+__global__ void maxpool3s2_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int C4 = C >> 2;
+    const size_t total = (size_t)B * Ho * Wo * C4;
+    if (i >= total) return;
+    const int c4 = (int)(i % C4);
+    size_t r = i / C4;
+    const int ox = (int)(r % Wo);
+    r /= Wo;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int iy = 2 * oy + dy;
+        if (iy < 0 || iy >= H) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int ix = 2 * ox + dx;
+            if (ix < 0 || ix >= W) continue;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + iy) * W + ix) * C) + c4);
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+    }
+    reinterpret_cast<float4*>(out + (((size_t)b * Ho + oy) * Wo + ox) * C)[c4] = m;
+}
+
+// 1x1 conv with few outputs (N <= 32): one warp per pixel, lanes stride over Cin.
+//   w: [N][Cin];  y[pix][n] = sum_c x[pix][c] * w[n][c] (+ bias[n]) (- shift[n])
+template <int N>
+__device__ __forceinline__ void smalln_dot(const float* __restrict__ x, const float* __restrict__ w, int Cin, int lane, float (&acc)[N]) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) acc[n] = 0.f;
+    for (int c = lane; c < Cin; c += 32) {
+        const float a = __ldg(x + c);
+#pragma unroll
+        for (int n = 0; n < N; ++n) acc[n] = fmaf(a, __ldg(w + (size_t)n * Cin + c), acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+}
+
+template <int N>
+__global__ void conv1x1_smalln_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                      const float* __restrict__ shift, float* __restrict__ y, size_t n_pix, int Cin) {
+    const size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pix >= n_pix) return;
+    float acc[N];
+    smalln_dot<N>(x + pix * Cin, w, Cin, lane, acc);
+    if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            float v = acc[n];
+            if (bias) v += bias[n];
+            if (shift) v -= shift[n];
+            y[pix * N + n] = v;
+        }
+    }
+}
+
+// CAM head (net/resnet50_cam.py:65-68): relu(conv1x1 2048->20) of sample 2p at (y,x) plus the same of the
+// flipped sample 2p+1 at (y, w-1-x).  feat NHWC [2P,h,w,Cin] -> out NCHW-like [P,20,h,w].
+__global__ void cam_head_kernel(const float* __restrict__ feat, const float* __restrict__ w, float* __restrict__ out, int P, int h,
+                                int wd, int Cin) {
+    const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const size_t n_pix = (size_t)P * h * wd;
+    if (wid >= n_pix) return;
+    const int x = (int)(wid % wd);
+    const int y = (int)((wid / wd) % h);
+    const int p = (int)(wid / ((size_t)wd * h));
+    float a0[20], a1[20];
+    smalln_dot<20>(feat + ((((size_t)(2 * p) * h + y) * wd) + x) * Cin, w, Cin, lane, a0);
+    smalln_dot<20>(feat + ((((size_t)(2 * p + 1) * h + y) * wd) + (wd - 1 - x)) * Cin, w, Cin, lane, a1);
+    if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < 20; ++n) out[(((size_t)p * 20 + n) * h + y) * wd + x] = fmaxf(a0[n], 0.f) + fmaxf(a1[n], 0.f);
+    }
+}
+
+// GroupNorm statistics (biased variance, eps added by the consumer): one block per (sample, group).
+// x NHWC [B,H,W,C]; stats[(b*G+g)*2 + {0,1}] = {mean, rstd}
+__global__ void gn_stats_kernel(const float* __restrict__ x, float* __restrict__ stats, int HW, int C, int G, float eps) {
+    const int b = blockIdx.x / G, g = blockIdx.x % G;
+    const int cpg = C / G;
+    const size_t n = (size_t)HW * cpg;
+    double s = 0.0, ss = 0.0;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const size_t pix = i / cpg;
+        const int c = (int)(i % cpg);
+        const double v = (double)x[((size_t)b * HW + pix) * C + g * cpg + c];
+        s += v;
+        ss += v * v;
+    }
+    __shared__ double sh[2][32];
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sh[0][threadIdx.x >> 5] = s;
+        sh[1][threadIdx.x >> 5] = ss;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[0][threadIdx.x] : 0.0;
+        ss = threadIdx.x < (blockDim.x >> 5) ? sh[1][threadIdx.x] : 0.0;
+        for (int o = 16; o; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        }
+        if (threadIdx.x == 0) {
+            const double mean = s / (double)n;
+            double var = ss / (double)n - mean * mean;
+            var = var < 0.0 ? 0.0 : var;
+            stats[2 * blockIdx.x] = (float)mean;
+            stats[2 * blockIdx.x + 1] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+    }
+}
+
+// GroupNorm affine -> bilinear upsample by `up` (align_corners=False) -> ReLU, written into a channel slice
+// of a concat buffer, cropped to (Hd, Wd)   (net/resnet50_irn.py:23-93,117-131: conv -> GN -> Upsample -> ReLU).
+__global__ void gn_up_relu_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float* __restrict__ dst, int B, int H, int W, int C, int G, int up,
+                                  int Hd, int Wd, int Cd, int coff) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)B * Hd * Wd * C;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int X = (int)(r % Wd);
+    r /= Wd;
+    const int Y = (int)(r % Hd);
+    const int b = (int)(r / Hd);
+    const int g = c / (C / G);
+    const float mean = stats[2 * (b * G + g)], rstd = stats[2 * (b * G + g) + 1];
+    const float ga = gamma[c], be = beta[c];
+    const float* xb = x + (size_t)b * H * W * C + c;
+    float v;
+    if (up == 1) {
+        v = (xb[((size_t)Y * W + X) * C] - mean) * rstd * ga + be;
+    } else {
+        const float inv = 1.0f / (float)up;
+        float sy = ((float)Y + 0.5f) * inv - 0.5f, sx = ((float)X + 0.5f) * inv - 0.5f;
+        sy = sy < 0.f ? 0.f : sy;
+        sx = sx < 0.f ? 0.f : sx;
+        int y0 = (int)sy, x0 = (int)sx;
+        y0 = y0 > H - 1 ? H - 1 : y0;
+        x0 = x0 > W - 1 ? W - 1 : x0;
+        const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
+        const float ly = sy - (float)y0, lx = sx - (float)x0;
+        const float v00 = (xb[((size_t)y0 * W + x0) * C] - mean) * rstd * ga + be;
+        const float v01 = (xb[((size_t)y0 * W + x1) * C] - mean) * rstd * ga + be;
+        const float v10 = (xb[((size_t)y1 * W + x0) * C] - mean) * rstd * ga + be;
+        const float v11 = (xb[((size_t)y1 * W + x1) * C] - mean) * rstd * ga + be;
+        v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    }
+    dst[(((size_t)b * Hd + Y) * Wd + X) * Cd + coff + c] = fmaxf(v, 0.f);
+}
+
+// EdgeDisplacement tail (net/resnet50_irn.py:228-234): crop to (fh,fw); edge = sigmoid(e0/2 + flip(e1)/2); dp = dp[0]
+//   e NHWC [2,Hf,Wf,1], d NHWC [2,Hf,Wf,2]  ->  edge [fh,fw], dp [2,fh,fw]
+__global__ void edge_dp_tail_kernel(const float* __restrict__ e, const float* __restrict__ d, float* __restrict__ edge,
+                                    float* __restrict__ dp, int Hf, int Wf, int fh, int fw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= fh * fw) return;
+    const int y = i / fw, x = i % fw;
+    const float a = e[(size_t)y * Wf + x] / 2.f + e[(size_t)Hf * Wf + (size_t)y * Wf + (fw - 1 - x)] / 2.f;
+    edge[i] = 1.f / (1.f + expf(-a));
+    dp[i] = d[((size_t)y * Wf + x) * 2];
+    dp[fh * fw + i] = d[((size_t)y * Wf + x) * 2 + 1];
+}
+
+}  // namespace irn

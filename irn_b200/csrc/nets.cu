@@ -1,0 +1,447 @@
+// C2/C3/I1/I2: ResNet-50 trunk, CAM head and IRNet edge/displacement heads as a native plan.
+//
+// Reference: net/resnet50.py:17-91 (Bottleneck / ResNet, strides (2,2,2,1)), net/resnet50_cam.py:55-70
+// (CAM.forward), net/resnet50_irn.py:23-133,216-234 (heads, MeanShift, EdgeDisplacement.forward).
+//
+// The plan owns the repacked weights on the device: FixedBatchNorm folded into (weight, bias), weights
+// transposed to [kh*kw*Cin][Cout] for the SIMT kernel.  Activations are NHWC fp32 in a caller-provided
+// workspace.  The host walks the fixed topology and enqueues kernels on the caller's stream; nothing
+// synchronises.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.h"
+#include "conv_simt.cuh"
+
+namespace irn {
+
+struct Conv {
+    int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
+    float* wt = nullptr;     // device [k*k*cin][cout]
+    float* bias = nullptr;   // device [cout] or null
+};
+
+struct Head {            // conv1x1 (no bias) -> GroupNorm(groups) -> [upsample] -> ReLU
+    Conv conv;
+    int groups = 1, up = 1;
+    float* gamma = nullptr;
+    float* beta = nullptr;
+};
+
+struct Block {
+    Conv c1, c2, c3, ds;
+    bool has_ds = false;
+};
+
+}  // namespace irn
+
+struct irn_net {
+    int kind = 0;   // 0 = CAM, 1 = IRN (EdgeDisplacement)
+    irn::Conv stem;
+    std::vector<irn::Block> blocks[4];
+    // CAM
+    float* classifier = nullptr;   // [20][2048]
+    // IRN
+    irn::Head edge[5], dp[7];
+    float* edge6_w = nullptr;      // [1][160]
+    float* edge6_b = nullptr;      // [1]
+    float* dp7_w = nullptr;        // [2][256]
+    float* mean_shift = nullptr;   // [2]
+    std::vector<void*> allocs;
+};
+
+namespace irn {
+
+static const int kPlanes[4] = {64, 128, 256, 512};
+static const int kBlocks[4] = {3, 4, 6, 3};
+static const int kStrides[4] = {1, 2, 2, 1};   // layer1..4 under the reference's strides=(2,2,2,1)
+
+struct Reader {
+    const float* p;
+    size_t left;
+    bool ok = true;
+    const float* take(size_t n) {
+        if (n > left) {
+            ok = false;
+            return nullptr;
+        }
+        const float* r = p;
+        p += n;
+        left -= n;
+        return r;
+    }
+};
+
+static int upload(irn_net* net, const std::vector<float>& h, float** out) {
+    void* d = nullptr;
+    IRN_CUDA(cudaMalloc(&d, h.size() * sizeof(float)));
+    net->allocs.push_back(d);
+    IRN_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    *out = (float*)d;
+    return kOk;
+}
+
+// Reads conv weight [cout][cin][k][k] (+ optional BN gamma, beta, mean, var) and uploads the folded,
+// transposed tensors.  Fold: y = (conv - mean) / sqrt(var + 1e-5) * gamma + beta  (net/resnet50.py:11-14).
+static int read_conv(irn_net* net, Reader& rd, Conv& c, int cin, int cout, int k, int stride, int pad, bool bn) {
+    c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; c.pad = pad;
+    const size_t nw = (size_t)cout * cin * k * k;
+    const float* w = rd.take(nw);
+    const float *ga = nullptr, *be = nullptr, *mu = nullptr, *va = nullptr;
+    if (bn) {
+        ga = rd.take(cout); be = rd.take(cout); mu = rd.take(cout); va = rd.take(cout);
+    }
+    if (!rd.ok) return fail(kBadArg, "parameter blob too short (conv %dx%d k%d)", cin, cout, k);
+    std::vector<float> wt(nw), bias;
+    std::vector<double> scale(cout, 1.0);
+    if (bn) {
+        bias.resize(cout);
+        for (int o = 0; o < cout; ++o) {
+            scale[o] = (double)ga[o] / std::sqrt((double)va[o] + 1e-5);
+            bias[o] = (float)((double)be[o] - (double)mu[o] * scale[o]);
+        }
+    }
+    for (int o = 0; o < cout; ++o)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int r = 0; r < k; ++r)
+                for (int s = 0; s < k; ++s)
+                    wt[((size_t)(r * k + s) * cin + ci) * cout + o] = (float)((double)w[(((size_t)o * cin + ci) * k + r) * k + s] * scale[o]);
+    int rc = upload(net, wt, &c.wt);
+    if (rc) return rc;
+    if (bn) rc = upload(net, bias, &c.bias);
+    return rc;
+}
+
+static int read_vec(irn_net* net, Reader& rd, size_t n, float** out) {
+    const float* p = rd.take(n);
+    if (!rd.ok) return fail(kBadArg, "parameter blob too short (vector of %zu)", n);
+    return upload(net, std::vector<float>(p, p + n), out);
+}
+
+static int read_trunk(irn_net* net, Reader& rd) {
+    int rc = read_conv(net, rd, net->stem, 3, 64, 7, 2, 3, true);
+    if (rc) return rc;
+    int cin = 64;
+    for (int l = 0; l < 4; ++l) {
+        net->blocks[l].resize(kBlocks[l]);
+        for (int b = 0; b < kBlocks[l]; ++b) {
+            Block& blk = net->blocks[l][b];
+            const int planes = kPlanes[l], stride = b == 0 ? kStrides[l] : 1;
+            if ((rc = read_conv(net, rd, blk.c1, cin, planes, 1, 1, 0, true))) return rc;
+            if ((rc = read_conv(net, rd, blk.c2, planes, planes, 3, stride, 1, true))) return rc;   // stride on conv2 (net/resnet50.py:24)
+            if ((rc = read_conv(net, rd, blk.c3, planes, planes * 4, 1, 1, 0, true))) return rc;
+            blk.has_ds = b == 0;
+            if (blk.has_ds && (rc = read_conv(net, rd, blk.ds, cin, planes * 4, 1, stride, 0, true))) return rc;
+            cin = planes * 4;
+        }
+    }
+    return kOk;
+}
+
+static int read_head(irn_net* net, Reader& rd, Head& h, int cin, int cout, int groups, int up) {
+    int rc = read_conv(net, rd, h.conv, cin, cout, 1, 1, 0, false);
+    if (rc) return rc;
+    h.groups = groups;
+    h.up = up;
+    if ((rc = read_vec(net, rd, cout, &h.gamma))) return rc;
+    return read_vec(net, rd, cout, &h.beta);
+}
+
+// ------------------------------------------------------------------ launch helpers
+static inline int conv_out(int n, int k, int s, int p) { return (n + 2 * p - k) / s + 1; }
+
+static int run_conv(const Conv& c, const float* in, int B, int H, int W, const float* residual, float* out, bool relu,
+                    cudaStream_t st, int* Ho_, int* Wo_) {
+    ConvGeom g;
+    g.B = B; g.H = H; g.W = W; g.Cin = c.cin;
+    g.Ho = conv_out(H, c.k, c.stride, c.pad);
+    g.Wo = conv_out(W, c.k, c.stride, c.pad);
+    g.Cout = c.cout; g.k = c.k; g.stride = c.stride; g.pad = c.pad;
+    const int M = B * g.Ho * g.Wo;
+    dim3 grid((M + kBM - 1) / kBM, (c.cout + kBN - 1) / kBN);
+    if (c.cin % 16 == 0)
+        conv_simt_kernel<true><<<grid, 256, 0, st>>>(in, c.wt, c.bias, residual, out, g, relu ? 1 : 0);
+    else
+        conv_simt_kernel<false><<<grid, 256, 0, st>>>(in, c.wt, c.bias, residual, out, g, relu ? 1 : 0);
+    IRN_LAUNCH_CHECK("conv_simt_kernel");
+    if (Ho_) *Ho_ = g.Ho;
+    if (Wo_) *Wo_ = g.Wo;
+    return kOk;
+}
+
+struct Arena {
+    char* base;
+    size_t size, off = 0;
+    bool ok = true;
+    float* take(size_t n_floats) {
+        const size_t bytes = align_up(n_floats * sizeof(float), 256);
+        if (off + bytes > size) {
+            ok = false;
+            return nullptr;
+        }
+        float* p = (float*)(base + off);
+        off += bytes;
+        return p;
+    }
+};
+
+struct TrunkShapes {
+    int H1, W1, H2, W2;          // after stem conv, after maxpool (= layer1 grid)
+    int Hl[4], Wl[4];            // output grid of layer1..4
+    size_t max_act;              // largest activation (floats) among stem out / block tensors
+};
+
+static TrunkShapes trunk_shapes(int B, int H, int W) {
+    TrunkShapes s;
+    s.H1 = conv_out(H, 7, 2, 3); s.W1 = conv_out(W, 7, 2, 3);
+    s.H2 = conv_out(s.H1, 3, 2, 1); s.W2 = conv_out(s.W1, 3, 2, 1);
+    int h = s.H2, w = s.W2;
+    s.max_act = (size_t)B * s.H1 * s.W1 * 64;
+    for (int l = 0; l < 4; ++l) {
+        // conv1 of the first block still runs on the incoming grid with `planes` channels
+        s.max_act = std::max(s.max_act, (size_t)B * h * w * kPlanes[l]);
+        h = conv_out(h, 3, kStrides[l], 1);
+        w = conv_out(w, 3, kStrides[l], 1);
+        s.Hl[l] = h; s.Wl[l] = w;
+        s.max_act = std::max(s.max_act, (size_t)B * h * w * kPlanes[l] * 4);
+    }
+    return s;
+}
+
+// Runs stem + maxpool + layer1..4.  feats[0] = after maxpool (x1 of IRNet), feats[1..4] = layer outputs.
+// When `keep` is set every feats[i] lives in its own arena buffer (IRNet taps them); otherwise buffers rotate.
+static int run_trunk(const irn_net* net, const float* x_nhwc, int B, int H, int W, Arena& ar, bool keep, const float* feats[5],
+                     TrunkShapes& sh, cudaStream_t st) {
+    sh = trunk_shapes(B, H, W);
+    float* stem_out = ar.take((size_t)B * sh.H1 * sh.W1 * 64);
+    float* pool_out = ar.take((size_t)B * sh.H2 * sh.W2 * 64);
+    float* t1 = ar.take(sh.max_act);
+    float* t2 = ar.take(sh.max_act);
+    float* dsb = ar.take(sh.max_act);
+    float* ping[2] = {ar.take(sh.max_act), ar.take(sh.max_act)};
+    if (!ar.ok) return fail(kWorkspace, "network workspace too small");
+    int rc;
+    if ((rc = run_conv(net->stem, x_nhwc, B, H, W, nullptr, stem_out, true, st, nullptr, nullptr))) return rc;
+    {
+        const size_t total = (size_t)B * sh.H2 * sh.W2 * 16;
+        maxpool3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(stem_out, pool_out, B, sh.H1, sh.W1, 64, sh.H2, sh.W2);
+        IRN_LAUNCH_CHECK("maxpool3s2_kernel");
+    }
+    feats[0] = pool_out;
+    const float* x = pool_out;
+    int h = sh.H2, w = sh.W2, flip = 0;
+    for (int l = 0; l < 4; ++l) {
+        const int nb = (int)net->blocks[l].size();
+        for (int b = 0; b < nb; ++b) {
+            const Block& blk = net->blocks[l][b];
+            int ho, wo;
+            if ((rc = run_conv(blk.c1, x, B, h, w, nullptr, t1, true, st, nullptr, nullptr))) return rc;
+            if ((rc = run_conv(blk.c2, t1, B, h, w, nullptr, t2, true, st, &ho, &wo))) return rc;
+            const float* res = x;
+            if (blk.has_ds) {
+                if ((rc = run_conv(blk.ds, x, B, h, w, nullptr, dsb, false, st, nullptr, nullptr))) return rc;
+                res = dsb;
+            }
+            float* out;
+            if (keep && b == nb - 1) {   // IRNet taps every stage output: give it a buffer of its own
+                out = ar.take((size_t)B * ho * wo * blk.c3.cout);
+                if (!ar.ok) return fail(kWorkspace, "network workspace too small");
+            } else {
+                out = ping[flip];
+                flip ^= 1;
+            }
+            if ((rc = run_conv(blk.c3, t2, B, ho, wo, res, out, true, st, nullptr, nullptr))) return rc;   // out += residual; relu (net/resnet50.py:51-52)
+            x = out;
+            h = ho;
+            w = wo;
+        }
+        feats[l + 1] = x;
+    }
+    return kOk;
+}
+
+static size_t trunk_workspace_floats(int B, int H, int W, bool keep) {
+    TrunkShapes s = trunk_shapes(B, H, W);
+    size_t n = (size_t)B * s.H1 * s.W1 * 64 + (size_t)B * s.H2 * s.W2 * 64 + 5 * s.max_act;
+    if (keep)
+        for (int l = 0; l < 4; ++l) n += (size_t)B * s.Hl[l] * s.Wl[l] * kPlanes[l] * 4;
+    return n + 64 * 32;   // alignment slack (256 B per buffer)
+}
+
+}  // namespace irn
+
+using namespace irn;
+
+extern "C" void irn_net_destroy(irn_net* net) {
+    if (!net) return;
+    for (void* p : net->allocs) cudaFree(p);
+    delete net;
+}
+
+extern "C" int irn_cam_net_create(const float* params, size_t n_floats, irn_net** out) {
+    if (!params || !out) return fail(kBadArg, "irn_cam_net_create: null pointer");
+    irn_net* net = new irn_net();
+    net->kind = 0;
+    Reader rd{params, n_floats};
+    int rc = read_trunk(net, rd);
+    if (!rc) rc = read_vec(net, rd, (size_t)20 * 2048, &net->classifier);
+    if (!rc && rd.left != 0) rc = fail(kBadArg, "irn_cam_net_create: %zu unread floats in the parameter blob", rd.left);
+    if (rc) {
+        irn_net_destroy(net);
+        return rc;
+    }
+    *out = net;
+    return kOk;
+}
+
+extern "C" int irn_irn_net_create(const float* params, size_t n_floats, irn_net** out) {
+    if (!params || !out) return fail(kBadArg, "irn_irn_net_create: null pointer");
+    irn_net* net = new irn_net();
+    net->kind = 1;
+    Reader rd{params, n_floats};
+    int rc = read_trunk(net, rd);
+    // heads in the order of net/resnet50_irn.py:23-93
+    static const int e_cin[5] = {64, 256, 512, 1024, 2048}, e_up[5] = {1, 1, 2, 4, 4};
+    for (int i = 0; i < 5 && !rc; ++i) rc = read_head(net, rd, net->edge[i], e_cin[i], 32, 4, e_up[i]);
+    if (!rc) rc = read_vec(net, rd, 160, &net->edge6_w);
+    if (!rc) rc = read_vec(net, rd, 1, &net->edge6_b);
+    static const int d_cin[7] = {64, 256, 512, 1024, 2048, 768, 448}, d_cout[7] = {64, 128, 256, 256, 256, 256, 256},
+                     d_g[7] = {8, 16, 16, 16, 16, 16, 16}, d_up[7] = {1, 1, 1, 2, 2, 2, 1};
+    for (int i = 0; i < 7 && !rc; ++i) rc = read_head(net, rd, net->dp[i], d_cin[i], d_cout[i], d_g[i], d_up[i]);
+    if (!rc) rc = read_vec(net, rd, 2 * 256, &net->dp7_w);
+    if (!rc) rc = read_vec(net, rd, 2, &net->mean_shift);
+    if (!rc && rd.left != 0) rc = fail(kBadArg, "irn_irn_net_create: %zu unread floats in the parameter blob", rd.left);
+    if (rc) {
+        irn_net_destroy(net);
+        return rc;
+    }
+    *out = net;
+    return kOk;
+}
+
+extern "C" size_t irn_cam_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || (B & 1) || H <= 0 || W <= 0) return 0;
+    return (trunk_workspace_floats(B, H, W, false) + (size_t)B * H * W * 3 + 64) * sizeof(float);
+}
+
+// CAM.forward for P = B/2 (image, flipped image) pairs: x NCHW fp32 [B,3,H,W] -> cam [P,20,ceil(H/16),ceil(W/16)]
+extern "C" int irn_cam_forward(const irn_net* net, const float* x_nchw, int B, int H, int W, float* cam_out, void* workspace,
+                               size_t workspace_bytes, irn_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    launch_counter() = 0;
+    if (!net || net->kind != 0 || !x_nchw || !cam_out || !workspace) return fail(kBadArg, "irn_cam_forward: bad argument");
+    if (B <= 0 || (B & 1) || H <= 0 || W <= 0) return fail(kBadArg, "irn_cam_forward: B must be a positive even number (image + flipped image), got B=%d H=%d W=%d", B, H, W);
+    if (((uintptr_t)workspace & 255) != 0) return fail(kBadArg, "irn_cam_forward: workspace must be 256-byte aligned");
+    Arena ar{(char*)workspace, workspace_bytes};
+    float* x_nhwc = ar.take((size_t)B * H * W * 3);
+    if (!ar.ok) return fail(kWorkspace, "irn_cam_forward: workspace too small");
+    {
+        const size_t total = (size_t)B * H * W * 3;
+        nchw_to_nhwc_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nchw, x_nhwc, B, 3, H, W, H, W);
+        IRN_LAUNCH_CHECK("nchw_to_nhwc_pad_kernel");
+    }
+    const float* feats[5];
+    TrunkShapes sh;
+    int rc = run_trunk(net, x_nhwc, B, H, W, ar, false, feats, sh, st);
+    if (rc) return rc;
+    const int P = B / 2, h = sh.Hl[3], w = sh.Wl[3];
+    const size_t warps = (size_t)P * h * w;
+    cam_head_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(feats[4], net->classifier, cam_out, P, h, w, 2048);
+    IRN_LAUNCH_CHECK("cam_head_kernel");
+    return kOk;
+}
+
+static size_t irn_head_floats(int B, const TrunkShapes& s) {
+    const size_t g2 = (size_t)B * s.Hl[0] * s.Wl[0];       // stride-4 grid (x1, x2)
+    const size_t g3 = (size_t)B * s.Hl[1] * s.Wl[1];       // stride-8 grid (x3)
+    size_t n = 0;
+    n += g2 * 256;                 // raw conv output scratch (largest head conv: 256 ch on the stride-4 grid)
+    n += g2 * 160;                 // edge concat
+    n += g3 * 768;                 // dp3|dp4|dp5 concat
+    n += g2 * 448;                 // dp1|dp2|dp_up3 concat
+    n += g2 * 256;                 // dp7 activations
+    n += g2 * 3;                   // edge logits + dp
+    n += (size_t)B * 16 * 2 + 64;  // GN stats
+    return n + 64 * 16;
+}
+
+extern "C" size_t irn_edge_displacement_workspace_bytes(int H, int W, int crop_size) {
+    if (H <= 0 || W <= 0 || H > crop_size || W > crop_size) return 0;
+    TrunkShapes s = trunk_shapes(2, crop_size, crop_size);
+    return (trunk_workspace_floats(2, crop_size, crop_size, true) + irn_head_floats(2, s) + (size_t)2 * crop_size * crop_size * 3 + 64) * sizeof(float);
+}
+
+static int run_head(const Head& hd, const float* x, int B, int H, int W, float* raw, float* stats, float* dst, int Hd, int Wd, int Cd,
+                    int coff, cudaStream_t st) {
+    int rc = run_conv(hd.conv, x, B, H, W, nullptr, raw, false, st, nullptr, nullptr);
+    if (rc) return rc;
+    gn_stats_kernel<<<B * hd.groups, 256, 0, st>>>(raw, stats, H * W, hd.conv.cout, hd.groups, 1e-5f);
+    IRN_LAUNCH_CHECK("gn_stats_kernel");
+    const size_t total = (size_t)B * Hd * Wd * hd.conv.cout;
+    gn_up_relu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(raw, stats, hd.gamma, hd.beta, dst, B, H, W, hd.conv.cout, hd.groups,
+                                                                      hd.up, Hd, Wd, Cd, coff);
+    IRN_LAUNCH_CHECK("gn_up_relu_kernel");
+    return kOk;
+}
+
+// EdgeDisplacement.forward: x NCHW fp32 [2,3,H,W] (image, flipped image) -> edge [1,fh,fw], dp [2,fh,fw],
+// fh = ceil(H/4), fw = ceil(W/4).  The input is zero-padded to crop_size x crop_size (net/resnet50_irn.py:226).
+extern "C" int irn_edge_displacement_forward(const irn_net* net, const float* x_nchw, int H, int W, int crop_size, float* edge_out,
+                                             float* dp_out, void* workspace, size_t workspace_bytes, irn_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    launch_counter() = 0;
+    if (!net || net->kind != 1 || !x_nchw || !edge_out || !dp_out || !workspace) return fail(kBadArg, "irn_edge_displacement_forward: bad argument");
+    if (H <= 0 || W <= 0 || H > crop_size || W > crop_size || (crop_size % 16) != 0)
+        return fail(kBadArg, "irn_edge_displacement_forward: need 0 < H,W <= crop_size (multiple of 16); got H=%d W=%d crop=%d", H, W, crop_size);
+    if (((uintptr_t)workspace & 255) != 0) return fail(kBadArg, "irn_edge_displacement_forward: workspace must be 256-byte aligned");
+    const int B = 2, S = crop_size;
+    Arena ar{(char*)workspace, workspace_bytes};
+    float* x_nhwc = ar.take((size_t)B * S * S * 3);
+    if (!ar.ok) return fail(kWorkspace, "irn_edge_displacement_forward: workspace too small");
+    {
+        const size_t total = (size_t)B * S * S * 3;
+        nchw_to_nhwc_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nchw, x_nhwc, B, 3, H, W, S, S);
+        IRN_LAUNCH_CHECK("nchw_to_nhwc_pad_kernel");
+    }
+    const float* f[5];
+    TrunkShapes sh;
+    int rc = run_trunk(net, x_nhwc, B, S, S, ar, true, f, sh, st);
+    if (rc) return rc;
+    const int h2 = sh.Hl[0], w2 = sh.Wl[0];   // stride 4 (x1, x2)
+    const int h3 = sh.Hl[1], w3 = sh.Wl[1];   // stride 8 (x3)
+    const int h4 = sh.Hl[2], w4 = sh.Wl[2];   // stride 16 (x4, x5)
+    const size_t g2 = (size_t)B * h2 * w2, g3 = (size_t)B * h3 * w3;
+    float* raw = ar.take(g2 * 256);
+    float* ecat = ar.take(g2 * 160);
+    float* dcat3 = ar.take(g3 * 768);
+    float* dcat2 = ar.take(g2 * 448);
+    float* dp7a = ar.take(g2 * 256);
+    float* elog = ar.take(g2);
+    float* dlog = ar.take(g2 * 2);
+    float* stats = ar.take((size_t)B * 16 * 2 + 64);
+    if (!ar.ok) return fail(kWorkspace, "irn_edge_displacement_forward: workspace too small");
+
+    // edge branch (net/resnet50_irn.py:117-122): every map lands on the stride-4 grid, cropped to edge2's size
+    const int eh[5] = {h2, h2, h3, h4, h4}, ew[5] = {w2, w2, w3, w4, w4};
+    for (int i = 0; i < 5; ++i)
+        if ((rc = run_head(net->edge[i], f[i], B, eh[i], ew[i], raw, stats, ecat, h2, w2, 160, 32 * i, st))) return rc;
+    conv1x1_smalln_kernel<1><<<(unsigned)((g2 * 32 + 255) / 256), 256, 0, st>>>(ecat, net->edge6_w, net->edge6_b, nullptr, elog, g2, 160);
+    IRN_LAUNCH_CHECK("conv1x1_smalln_kernel<1>");
+
+    // displacement branch (net/resnet50_irn.py:124-131)
+    if ((rc = run_head(net->dp[0], f[0], B, h2, w2, raw, stats, dcat2, h2, w2, 448, 0, st))) return rc;      // dp1 64
+    if ((rc = run_head(net->dp[1], f[1], B, h2, w2, raw, stats, dcat2, h2, w2, 448, 64, st))) return rc;     // dp2 128
+    if ((rc = run_head(net->dp[2], f[2], B, h3, w3, raw, stats, dcat3, h3, w3, 768, 0, st))) return rc;      // dp3
+    if ((rc = run_head(net->dp[3], f[3], B, h4, w4, raw, stats, dcat3, h3, w3, 768, 256, st))) return rc;    // dp4 up x2, crop to dp3
+    if ((rc = run_head(net->dp[4], f[4], B, h4, w4, raw, stats, dcat3, h3, w3, 768, 512, st))) return rc;    // dp5 up x2
+    if ((rc = run_head(net->dp[5], dcat3, B, h3, w3, raw, stats, dcat2, h2, w2, 448, 192, st))) return rc;   // dp6 up x2, crop to dp2
+    if ((rc = run_head(net->dp[6], dcat2, B, h2, w2, raw, stats, dp7a, h2, w2, 256, 0, st))) return rc;      // dp7 conv/GN/ReLU
+    conv1x1_smalln_kernel<2><<<(unsigned)((g2 * 32 + 255) / 256), 256, 0, st>>>(dp7a, net->dp7_w, nullptr, net->mean_shift, dlog, g2, 256);
+    IRN_LAUNCH_CHECK("conv1x1_smalln_kernel<2>");
+
+    const int fh = (H - 1) / 4 + 1, fw = (W - 1) / 4 + 1;
+    edge_dp_tail_kernel<<<(fh * fw + 255) / 256, 256, 0, st>>>(elog, dlog, edge_out, dp_out, h2, w2, fh, fw);
+    IRN_LAUNCH_CHECK("edge_dp_tail_kernel");
+    return kOk;
+}

@@ -230,8 +230,15 @@ constexpr int kSW = kTX + 2 * kR;     // 40 columns staged (x0-4 .. x0+35)
 constexpr int kYH = kTY + 2 * kR;     // 24 state rows staged (y0-4 .. y0+19)
 constexpr int kWH = kTY + kR;         // 20 weight rows staged (y0-4 .. y0+15): mirrored taps only look up / left
 constexpr int kMaxClsPlanes = 9;
-constexpr int kMaxCH = 4;
 constexpr int kWBufFloats = kMaxClsPlanes * kWH * kSW;   // 7200 floats = 28.8 KB per buffer
+
+// fp32 -> fp64 widening of a non-negative finite weight with three integer-pipe ops instead of F2F.F64.F32
+// (measured: the 68 conversions per pixel per step were the kernel's bottleneck).  Exact for normal
+// values; +0 and sub-normals (< 1.2e-38) map to <= 2^-126, i.e. they stay numerically zero.
+__device__ __forceinline__ double widen_weight(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return __hiloint2double((int)((u >> 3) + 0x38000000u), (int)(u << 29));
+}
 
 constexpr size_t rw_tma_smem_bytes(int ch) {
     return 128 /*alignment slack*/ + (size_t)ch * kYH * kSW * sizeof(double) + 2 * (size_t)kWBufFloats * sizeof(float) + 64;
@@ -322,11 +329,11 @@ rw_step_tma_kernel(const __grid_constant__ RwMaps maps, const double* __restrict
                         constexpr int kf = plane5(dy, dxc);
                         constexpr int kb = plane5(-dy, -dxc);
                         if constexpr (kf >= 0) {
-                            const double wv = (double)wb[((kf - cls_base5(cls)) * kWH + ty0 + j + kR) * kSW + lane + kR];
+                            const double wv = widen_weight(wb[((kf - cls_base5(cls)) * kWH + ty0 + j + kR) * kSW + lane + kR]);
 #pragma unroll
                             for (int c = 0; c < CH; ++c) acc[j][c] = fma(wv, v[c], acc[j][c]);
                         } else if constexpr (kb >= 0) {
-                            const double wv = (double)wb[((kb - cls_base5(cls)) * kWH + ty0 + r + kR) * kSW + lane + dxc + kR];
+                            const double wv = widen_weight(wb[((kb - cls_base5(cls)) * kWH + ty0 + r + kR) * kSW + lane + dxc + kR]);
 #pragma unroll
                             for (int c = 0; c < CH; ++c) acc[j][c] = fma(wv, v[c], acc[j][c]);
                         }
