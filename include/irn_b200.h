@@ -120,6 +120,21 @@ typedef struct irn_net irn_net;
 int irn_cam_net_create(const float* params, size_t n_floats, irn_net** out);
 int irn_irn_net_create(const float* params, size_t n_floats, irn_net** out);
 void irn_net_destroy(irn_net* net);
+/* Convolution arithmetic: 1 (default) = tcgen05 tensor cores, 3xTF32 split (fp32-grade, error ~5e-7 per
+ * product) for every conv with Cin % 32 == 0 and Cout % 64 == 0, SIMT fp32 for the rest; 0 = SIMT IEEE fp32
+ * everywhere (the on-device cross-check). */
+int irn_net_set_conv_mode(irn_net* net, int mode);
+
+/* One convolution (+ folded FixedBatchNorm, residual add, ReLU) as a plan of its own: the building block of
+ * the two networks above (net/resnet50.py:34-54), exposed for unit tests and for wiring other topologies.
+ *   weight_oihw HOST fp32 [cout,cin,k,k]; bn4 HOST fp32 [4,cout] = gamma,beta,running_mean,running_var or NULL.
+ *   forward: in NHWC fp32 [B,H,W,cin] -> out NHWC [B,Ho,Wo,cout]; residual NHWC like out, or NULL. */
+typedef struct irn_conv irn_conv;
+int irn_conv_create(const float* weight_oihw, const float* bn4, int cin, int cout, int k, int stride,
+                    int pad, irn_conv** out);
+void irn_conv_destroy(irn_conv* conv);
+int irn_conv_forward(irn_conv* conv, const float* in, int B, int H, int W, const float* residual,
+                     float* out, int relu, int mode, irn_stream_t stream);
 
 /* CAM.forward over B/2 (image, horizontally flipped image) pairs.
  *   x_nchw fp32 [B,3,H,W] (device), B even -> cam fp32 [B/2,20,ceil(H/16),ceil(W/16)]:
@@ -128,14 +143,25 @@ size_t irn_cam_workspace_bytes(int B, int H, int W);
 int irn_cam_forward(const irn_net* net, const float* x_nchw, int B, int H, int W, float* cam_out,
                     void* workspace, size_t workspace_bytes, irn_stream_t stream);
 
-/* EdgeDisplacement.forward for one (image, flipped image) pair.
- *   x_nchw fp32 [2,3,H,W]; zero-padded to crop_size (net/resnet50_irn.py:226) ->
- *   edge fp32 [1,fh,fw] = sigmoid(e[0]/2 + e[1].flip(-1)/2), dp fp32 [2,fh,fw] = dp[0] - running_mean;
- *   fh = ceil(H/4), fw = ceil(W/4). */
-size_t irn_edge_displacement_workspace_bytes(int H, int W, int crop_size);
-int irn_edge_displacement_forward(const irn_net* net, const float* x_nchw, int H, int W,
+/* EdgeDisplacement.forward for P (image, flipped image) pairs of equal size.
+ *   x_nchw fp32 [2P,3,H,W]; zero-padded to crop_size (net/resnet50_irn.py:226) ->
+ *   edge fp32 [P,1,fh,fw] = sigmoid(e[2p]/2 + e[2p+1].flip(-1)/2), dp fp32 [P,2,fh,fw] = dp[2p] - running_mean;
+ *   fh = ceil(H/4), fw = ceil(W/4).  The reference runs P = 1. */
+size_t irn_edge_displacement_workspace_bytes(int P, int H, int W, int crop_size);
+int irn_edge_displacement_forward(const irn_net* net, const float* x_nchw, int P, int H, int W,
                                   int crop_size, float* edge_out, float* dp_out, void* workspace,
                                   size_t workspace_bytes, irn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * C4  multi-scale CAM merge.  Replaces step/make_cam.py:38-52.
+ *   cams: HOST array of n_scales DEVICE pointers, each fp32 [20,hs[s],ws[s]] (CAM.forward outputs);
+ *   (H,W) original image size; keys_dev device int32 [K] = classes present (torch.nonzero(label));
+ *   strided_out fp32 [K,ceil(H/4),ceil(W/4)], highres_out fp32 [K,H,W] (either may be NULL):
+ *   sum over scales of the bilinear (align_corners=False) resample, each kept class / (max + 1e-5).
+ *   scratch: device, >= 2*K*4 bytes. */
+int irn_cam_merge(const float* const* cams, const int* hs, const int* ws, int n_scales, int H, int W,
+                  const int32_t* keys_dev, int K, float* strided_out, float* highres_out,
+                  void* scratch, irn_stream_t stream);
 
 #ifdef __cplusplus
 }

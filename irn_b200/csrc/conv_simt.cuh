@@ -314,17 +314,23 @@ __global__ void gn_up_relu_kernel(const float* __restrict__ x, const float* __re
     dst[(((size_t)b * Hd + Y) * Wd + X) * Cd + coff + c] = fmaxf(v, 0.f);
 }
 
-// EdgeDisplacement tail (net/resnet50_irn.py:228-234): crop to (fh,fw); edge = sigmoid(e0/2 + flip(e1)/2); dp = dp[0]
-//   e NHWC [2,Hf,Wf,1], d NHWC [2,Hf,Wf,2]  ->  edge [fh,fw], dp [2,fh,fw]
+// EdgeDisplacement tail (net/resnet50_irn.py:228-234) for pair p = blockIdx.y: crop to (fh,fw);
+// edge = sigmoid(e[2p]/2 + flip(e[2p+1])/2); dp = dp[2p]
+//   e NHWC [2P,Hf,Wf,1], d NHWC [2P,Hf,Wf,2]  ->  edge [P,fh,fw], dp [P,2,fh,fw]
 __global__ void edge_dp_tail_kernel(const float* __restrict__ e, const float* __restrict__ d, float* __restrict__ edge,
                                     float* __restrict__ dp, int Hf, int Wf, int fh, int fw) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.y;
     if (i >= fh * fw) return;
     const int y = i / fw, x = i % fw;
-    const float a = e[(size_t)y * Wf + x] / 2.f + e[(size_t)Hf * Wf + (size_t)y * Wf + (fw - 1 - x)] / 2.f;
-    edge[i] = 1.f / (1.f + expf(-a));
-    dp[i] = d[((size_t)y * Wf + x) * 2];
-    dp[fh * fw + i] = d[((size_t)y * Wf + x) * 2 + 1];
+    const size_t plane = (size_t)Hf * Wf;
+    const float* e0 = e + (size_t)(2 * p) * plane;
+    const float* e1 = e0 + plane;
+    const float* d0 = d + (size_t)(2 * p) * plane * 2;
+    const float a = e0[(size_t)y * Wf + x] / 2.f + e1[(size_t)y * Wf + (fw - 1 - x)] / 2.f;
+    edge[(size_t)p * fh * fw + i] = 1.f / (1.f + expf(-a));
+    dp[((size_t)p * 2) * fh * fw + i] = d0[((size_t)y * Wf + x) * 2];
+    dp[((size_t)p * 2 + 1) * fh * fw + i] = d0[((size_t)y * Wf + x) * 2 + 1];
 }
 
 }  // namespace irn

@@ -13,13 +13,19 @@
 
 #include "common.h"
 #include "conv_simt.cuh"
+#include "conv_tc.cuh"
 
 namespace irn {
 
 struct Conv {
     int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
-    float* wt = nullptr;     // device [k*k*cin][cout]
+    float* wt = nullptr;     // device [k*k*cin][cout]   (SIMT kernel)
     float* bias = nullptr;   // device [cout] or null
+    // tensor-core path: weights [cout][k*k*cin] split into tf32 hi / lo parts
+    float* w_hi = nullptr;
+    float* w_lo = nullptr;
+    int bn = 0;              // N tile (64 or 128); 0 = not eligible
+    CUtensorMap map_bhi, map_blo;
 };
 
 struct Head {            // conv1x1 (no bias) -> GroupNorm(groups) -> [upsample] -> ReLU
@@ -38,6 +44,7 @@ struct Block {
 
 struct irn_net {
     int kind = 0;   // 0 = CAM, 1 = IRN (EdgeDisplacement)
+    int conv_mode = 1;   // 0 = SIMT exact-fp32 convolutions only, 1 = tcgen05 3xTF32 where eligible
     irn::Conv stem;
     std::vector<irn::Block> blocks[4];
     // CAM
@@ -109,8 +116,35 @@ static int read_conv(irn_net* net, Reader& rd, Conv& c, int cin, int cout, int k
                     wt[((size_t)(r * k + s) * cin + ci) * cout + o] = (float)((double)w[(((size_t)o * cin + ci) * k + r) * k + s] * scale[o]);
     int rc = upload(net, wt, &c.wt);
     if (rc) return rc;
-    if (bn) rc = upload(net, bias, &c.bias);
-    return rc;
+    if (bn && (rc = upload(net, bias, &c.bias))) return rc;
+    // tensor-core eligibility: 32-channel k slices, 64/128-wide N tiles, 1x1 or 3x3, stride 1 or 2
+    c.bn = (cout % 128 == 0) ? 128 : (cout % 64 == 0 ? 64 : 0);
+    if (cin % kTcBK != 0 || !(k == 1 || k == 3) || !(stride == 1 || stride == 2)) c.bn = 0;
+    if (c.bn) {
+        const size_t K = (size_t)k * k * cin;
+        std::vector<float> hi(nw), lo(nw);
+        for (int o = 0; o < cout; ++o)
+            for (size_t kk = 0; kk < K; ++kk) {
+                const float v = wt[kk * cout + o];
+                uint32_t u;
+                std::memcpy(&u, &v, 4);
+                // round-to-nearest (ties away) to 10 explicit mantissa bits, like cvt.rna.tf32.f32
+                uint32_t h = (u + 0x1000u) & 0xFFFFE000u;
+                float hf;
+                std::memcpy(&hf, &h, 4);
+                if (!std::isfinite(hf)) hf = v;
+                hi[(size_t)o * K + kk] = hf;
+                lo[(size_t)o * K + kk] = v - hf;
+            }
+        if ((rc = upload(net, hi, &c.w_hi))) return rc;
+        if ((rc = upload(net, lo, &c.w_lo))) return rc;
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)cout};
+        const uint64_t strides[1] = {(uint64_t)K * sizeof(float)};
+        const uint32_t box[2] = {(uint32_t)kTcBK, (uint32_t)c.bn};
+        if ((rc = make_tensor_map(&c.map_bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tensor_map(&c.map_blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    }
+    return kOk;
 }
 
 static int read_vec(irn_net* net, Reader& rd, size_t n, float** out) {
@@ -151,13 +185,46 @@ static int read_head(irn_net* net, Reader& rd, Head& h, int cin, int cout, int g
 // ------------------------------------------------------------------ launch helpers
 static inline int conv_out(int n, int k, int s, int p) { return (n + 2 * p - k) / s + 1; }
 
-static int run_conv(const Conv& c, const float* in, int B, int H, int W, const float* residual, float* out, bool relu,
+template <int BN>
+static int launch_tc(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
+                     cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        IRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(BN)));
+        attr_set = true;
+    }
+    TcMaps maps;
+    maps.b_hi = c.map_bhi;
+    maps.b_lo = c.map_blo;
+    const uint64_t dims[4] = {(uint64_t)c.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)c.cin * 4, (uint64_t)W * c.cin * 4, (uint64_t)H * W * c.cin * 4};
+    const uint32_t box[4] = {(uint32_t)kTcBK, (uint32_t)(kTcTW * c.stride), (uint32_t)(kTcTH * c.stride), 1};
+    const uint32_t estr[4] = {1, (uint32_t)c.stride, (uint32_t)c.stride, 1};
+    int rc = make_tensor_map(&maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, estr);
+    if (rc) return rc;
+    TcArgs a;
+    a.bias = c.bias; a.residual = residual; a.out = out;
+    a.B = B; a.Ho = Ho; a.Wo = Wo; a.Cout = c.cout; a.Cin = c.cin; a.ksize = c.k; a.stride = c.stride; a.pad = c.pad;
+    a.relu = relu ? 1 : 0;
+    a.tiles_x = (Wo + kTcTW - 1) / kTcTW;
+    a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
+    dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B), (unsigned)(c.cout / BN));
+    conv_tc_kernel<BN><<<grid, kTcThreads, tc_smem_bytes(BN), st>>>(maps, a);
+    IRN_LAUNCH_CHECK("conv_tc_kernel");
+    return kOk;
+}
+
+static int run_conv(const irn_net* net, const Conv& c, const float* in, int B, int H, int W, const float* residual, float* out, bool relu,
                     cudaStream_t st, int* Ho_, int* Wo_) {
     ConvGeom g;
     g.B = B; g.H = H; g.W = W; g.Cin = c.cin;
     g.Ho = conv_out(H, c.k, c.stride, c.pad);
     g.Wo = conv_out(W, c.k, c.stride, c.pad);
     g.Cout = c.cout; g.k = c.k; g.stride = c.stride; g.pad = c.pad;
+    if (Ho_) *Ho_ = g.Ho;
+    if (Wo_) *Wo_ = g.Wo;
+    if (net->conv_mode == 1 && c.bn == 128) return launch_tc<128>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
+    if (net->conv_mode == 1 && c.bn == 64) return launch_tc<64>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
     const int M = B * g.Ho * g.Wo;
     dim3 grid((M + kBM - 1) / kBM, (c.cout + kBN - 1) / kBN);
     if (c.cin % 16 == 0)
@@ -165,8 +232,6 @@ static int run_conv(const Conv& c, const float* in, int B, int H, int W, const f
     else
         conv_simt_kernel<false><<<grid, 256, 0, st>>>(in, c.wt, c.bias, residual, out, g, relu ? 1 : 0);
     IRN_LAUNCH_CHECK("conv_simt_kernel");
-    if (Ho_) *Ho_ = g.Ho;
-    if (Wo_) *Wo_ = g.Wo;
     return kOk;
 }
 
@@ -222,7 +287,7 @@ static int run_trunk(const irn_net* net, const float* x_nhwc, int B, int H, int 
     float* ping[2] = {ar.take(sh.max_act), ar.take(sh.max_act)};
     if (!ar.ok) return fail(kWorkspace, "network workspace too small");
     int rc;
-    if ((rc = run_conv(net->stem, x_nhwc, B, H, W, nullptr, stem_out, true, st, nullptr, nullptr))) return rc;
+    if ((rc = run_conv(net, net->stem, x_nhwc, B, H, W, nullptr, stem_out, true, st, nullptr, nullptr))) return rc;
     {
         const size_t total = (size_t)B * sh.H2 * sh.W2 * 16;
         maxpool3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(stem_out, pool_out, B, sh.H1, sh.W1, 64, sh.H2, sh.W2);
@@ -236,11 +301,11 @@ static int run_trunk(const irn_net* net, const float* x_nhwc, int B, int H, int 
         for (int b = 0; b < nb; ++b) {
             const Block& blk = net->blocks[l][b];
             int ho, wo;
-            if ((rc = run_conv(blk.c1, x, B, h, w, nullptr, t1, true, st, nullptr, nullptr))) return rc;
-            if ((rc = run_conv(blk.c2, t1, B, h, w, nullptr, t2, true, st, &ho, &wo))) return rc;
+            if ((rc = run_conv(net, blk.c1, x, B, h, w, nullptr, t1, true, st, nullptr, nullptr))) return rc;
+            if ((rc = run_conv(net, blk.c2, t1, B, h, w, nullptr, t2, true, st, &ho, &wo))) return rc;
             const float* res = x;
             if (blk.has_ds) {
-                if ((rc = run_conv(blk.ds, x, B, h, w, nullptr, dsb, false, st, nullptr, nullptr))) return rc;
+                if ((rc = run_conv(net, blk.ds, x, B, h, w, nullptr, dsb, false, st, nullptr, nullptr))) return rc;
                 res = dsb;
             }
             float* out;
@@ -251,7 +316,7 @@ static int run_trunk(const irn_net* net, const float* x_nhwc, int B, int H, int 
                 out = ping[flip];
                 flip ^= 1;
             }
-            if ((rc = run_conv(blk.c3, t2, B, ho, wo, res, out, true, st, nullptr, nullptr))) return rc;   // out += residual; relu (net/resnet50.py:51-52)
+            if ((rc = run_conv(net, blk.c3, t2, B, ho, wo, res, out, true, st, nullptr, nullptr))) return rc;   // out += residual; relu (net/resnet50.py:51-52)
             x = out;
             h = ho;
             w = wo;
@@ -272,6 +337,52 @@ static size_t trunk_workspace_floats(int B, int H, int W, bool keep) {
 }  // namespace irn
 
 using namespace irn;
+
+// ---- single convolution as a plan of its own (unit tests / integration of other networks)
+struct irn_conv {
+    irn_net holder;   // owns the device allocations
+    irn::Conv conv;
+};
+
+extern "C" int irn_conv_create(const float* weight_oihw, const float* bn4 /* gamma,beta,mean,var or NULL */, int cin, int cout, int k,
+                               int stride, int pad, irn_conv** out) {
+    if (!weight_oihw || !out || cin <= 0 || cout <= 0 || k <= 0 || stride <= 0 || pad < 0) return fail(kBadArg, "irn_conv_create: bad argument");
+    const size_t nw = (size_t)cout * cin * k * k;
+    std::vector<float> blob(weight_oihw, weight_oihw + nw);
+    if (bn4) blob.insert(blob.end(), bn4, bn4 + 4 * (size_t)cout);
+    irn_conv* c = new irn_conv();
+    Reader rd{blob.data(), blob.size()};
+    int rc = read_conv(&c->holder, rd, c->conv, cin, cout, k, stride, pad, bn4 != nullptr);
+    if (rc) {
+        for (void* p : c->holder.allocs) cudaFree(p);
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return kOk;
+}
+
+extern "C" void irn_conv_destroy(irn_conv* c) {
+    if (!c) return;
+    for (void* p : c->holder.allocs) cudaFree(p);
+    delete c;
+}
+
+// in NHWC fp32 [B,H,W,cin] -> out NHWC [B,Ho,Wo,cout]; residual NHWC like out or NULL; mode as irn_net_set_conv_mode
+extern "C" int irn_conv_forward(irn_conv* c, const float* in, int B, int H, int W, const float* residual, float* out, int relu, int mode,
+                                irn_stream_t stream) {
+    launch_counter() = 0;
+    if (!c || !in || !out || B <= 0 || H <= 0 || W <= 0) return fail(kBadArg, "irn_conv_forward: bad argument");
+    if (mode == 1 && c->conv.bn == 0) return fail(kUnsupported, "irn_conv_forward: this convolution is not eligible for the tensor-core kernel (Cin %% 32, Cout %% 64, k in {1,3}, stride in {1,2})");
+    c->holder.conv_mode = mode;
+    return run_conv(&c->holder, c->conv, in, B, H, W, residual, out, relu != 0, (cudaStream_t)stream, nullptr, nullptr);
+}
+
+extern "C" int irn_net_set_conv_mode(irn_net* net, int mode) {
+    if (!net || (mode != 0 && mode != 1)) return fail(kBadArg, "irn_net_set_conv_mode: mode must be 0 (SIMT fp32) or 1 (tcgen05 3xTF32)");
+    net->conv_mode = mode;
+    return kOk;
+}
 
 extern "C" void irn_net_destroy(irn_net* net) {
     if (!net) return;
@@ -366,15 +477,16 @@ static size_t irn_head_floats(int B, const TrunkShapes& s) {
     return n + 64 * 16;
 }
 
-extern "C" size_t irn_edge_displacement_workspace_bytes(int H, int W, int crop_size) {
-    if (H <= 0 || W <= 0 || H > crop_size || W > crop_size) return 0;
-    TrunkShapes s = trunk_shapes(2, crop_size, crop_size);
-    return (trunk_workspace_floats(2, crop_size, crop_size, true) + irn_head_floats(2, s) + (size_t)2 * crop_size * crop_size * 3 + 64) * sizeof(float);
+extern "C" size_t irn_edge_displacement_workspace_bytes(int P, int H, int W, int crop_size) {
+    if (P <= 0 || H <= 0 || W <= 0 || H > crop_size || W > crop_size) return 0;
+    const int B = 2 * P;
+    TrunkShapes s = trunk_shapes(B, crop_size, crop_size);
+    return (trunk_workspace_floats(B, crop_size, crop_size, true) + irn_head_floats(B, s) + (size_t)B * crop_size * crop_size * 3 + 64) * sizeof(float);
 }
 
-static int run_head(const Head& hd, const float* x, int B, int H, int W, float* raw, float* stats, float* dst, int Hd, int Wd, int Cd,
+static int run_head(const irn_net* net, const Head& hd, const float* x, int B, int H, int W, float* raw, float* stats, float* dst, int Hd, int Wd, int Cd,
                     int coff, cudaStream_t st) {
-    int rc = run_conv(hd.conv, x, B, H, W, nullptr, raw, false, st, nullptr, nullptr);
+    int rc = run_conv(net, hd.conv, x, B, H, W, nullptr, raw, false, st, nullptr, nullptr);
     if (rc) return rc;
     gn_stats_kernel<<<B * hd.groups, 256, 0, st>>>(raw, stats, H * W, hd.conv.cout, hd.groups, 1e-5f);
     IRN_LAUNCH_CHECK("gn_stats_kernel");
@@ -387,15 +499,15 @@ static int run_head(const Head& hd, const float* x, int B, int H, int W, float* 
 
 // EdgeDisplacement.forward: x NCHW fp32 [2,3,H,W] (image, flipped image) -> edge [1,fh,fw], dp [2,fh,fw],
 // fh = ceil(H/4), fw = ceil(W/4).  The input is zero-padded to crop_size x crop_size (net/resnet50_irn.py:226).
-extern "C" int irn_edge_displacement_forward(const irn_net* net, const float* x_nchw, int H, int W, int crop_size, float* edge_out,
+extern "C" int irn_edge_displacement_forward(const irn_net* net, const float* x_nchw, int P, int H, int W, int crop_size, float* edge_out,
                                              float* dp_out, void* workspace, size_t workspace_bytes, irn_stream_t stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     launch_counter() = 0;
     if (!net || net->kind != 1 || !x_nchw || !edge_out || !dp_out || !workspace) return fail(kBadArg, "irn_edge_displacement_forward: bad argument");
-    if (H <= 0 || W <= 0 || H > crop_size || W > crop_size || (crop_size % 16) != 0)
-        return fail(kBadArg, "irn_edge_displacement_forward: need 0 < H,W <= crop_size (multiple of 16); got H=%d W=%d crop=%d", H, W, crop_size);
+    if (P <= 0 || H <= 0 || W <= 0 || H > crop_size || W > crop_size || (crop_size % 16) != 0)
+        return fail(kBadArg, "irn_edge_displacement_forward: need P > 0 and 0 < H,W <= crop_size (multiple of 16); got P=%d H=%d W=%d crop=%d", P, H, W, crop_size);
     if (((uintptr_t)workspace & 255) != 0) return fail(kBadArg, "irn_edge_displacement_forward: workspace must be 256-byte aligned");
-    const int B = 2, S = crop_size;
+    const int B = 2 * P, S = crop_size;
     Arena ar{(char*)workspace, workspace_bytes};
     float* x_nhwc = ar.take((size_t)B * S * S * 3);
     if (!ar.ok) return fail(kWorkspace, "irn_edge_displacement_forward: workspace too small");
@@ -425,23 +537,23 @@ extern "C" int irn_edge_displacement_forward(const irn_net* net, const float* x_
     // edge branch (net/resnet50_irn.py:117-122): every map lands on the stride-4 grid, cropped to edge2's size
     const int eh[5] = {h2, h2, h3, h4, h4}, ew[5] = {w2, w2, w3, w4, w4};
     for (int i = 0; i < 5; ++i)
-        if ((rc = run_head(net->edge[i], f[i], B, eh[i], ew[i], raw, stats, ecat, h2, w2, 160, 32 * i, st))) return rc;
+        if ((rc = run_head(net, net->edge[i], f[i], B, eh[i], ew[i], raw, stats, ecat, h2, w2, 160, 32 * i, st))) return rc;
     conv1x1_smalln_kernel<1><<<(unsigned)((g2 * 32 + 255) / 256), 256, 0, st>>>(ecat, net->edge6_w, net->edge6_b, nullptr, elog, g2, 160);
     IRN_LAUNCH_CHECK("conv1x1_smalln_kernel<1>");
 
     // displacement branch (net/resnet50_irn.py:124-131)
-    if ((rc = run_head(net->dp[0], f[0], B, h2, w2, raw, stats, dcat2, h2, w2, 448, 0, st))) return rc;      // dp1 64
-    if ((rc = run_head(net->dp[1], f[1], B, h2, w2, raw, stats, dcat2, h2, w2, 448, 64, st))) return rc;     // dp2 128
-    if ((rc = run_head(net->dp[2], f[2], B, h3, w3, raw, stats, dcat3, h3, w3, 768, 0, st))) return rc;      // dp3
-    if ((rc = run_head(net->dp[3], f[3], B, h4, w4, raw, stats, dcat3, h3, w3, 768, 256, st))) return rc;    // dp4 up x2, crop to dp3
-    if ((rc = run_head(net->dp[4], f[4], B, h4, w4, raw, stats, dcat3, h3, w3, 768, 512, st))) return rc;    // dp5 up x2
-    if ((rc = run_head(net->dp[5], dcat3, B, h3, w3, raw, stats, dcat2, h2, w2, 448, 192, st))) return rc;   // dp6 up x2, crop to dp2
-    if ((rc = run_head(net->dp[6], dcat2, B, h2, w2, raw, stats, dp7a, h2, w2, 256, 0, st))) return rc;      // dp7 conv/GN/ReLU
+    if ((rc = run_head(net, net->dp[0], f[0], B, h2, w2, raw, stats, dcat2, h2, w2, 448, 0, st))) return rc;      // dp1 64
+    if ((rc = run_head(net, net->dp[1], f[1], B, h2, w2, raw, stats, dcat2, h2, w2, 448, 64, st))) return rc;     // dp2 128
+    if ((rc = run_head(net, net->dp[2], f[2], B, h3, w3, raw, stats, dcat3, h3, w3, 768, 0, st))) return rc;      // dp3
+    if ((rc = run_head(net, net->dp[3], f[3], B, h4, w4, raw, stats, dcat3, h3, w3, 768, 256, st))) return rc;    // dp4 up x2, crop to dp3
+    if ((rc = run_head(net, net->dp[4], f[4], B, h4, w4, raw, stats, dcat3, h3, w3, 768, 512, st))) return rc;    // dp5 up x2
+    if ((rc = run_head(net, net->dp[5], dcat3, B, h3, w3, raw, stats, dcat2, h2, w2, 448, 192, st))) return rc;   // dp6 up x2, crop to dp2
+    if ((rc = run_head(net, net->dp[6], dcat2, B, h2, w2, raw, stats, dp7a, h2, w2, 256, 0, st))) return rc;      // dp7 conv/GN/ReLU
     conv1x1_smalln_kernel<2><<<(unsigned)((g2 * 32 + 255) / 256), 256, 0, st>>>(dp7a, net->dp7_w, nullptr, net->mean_shift, dlog, g2, 256);
     IRN_LAUNCH_CHECK("conv1x1_smalln_kernel<2>");
 
     const int fh = (H - 1) / 4 + 1, fw = (W - 1) / 4 + 1;
-    edge_dp_tail_kernel<<<(fh * fw + 255) / 256, 256, 0, st>>>(elog, dlog, edge_out, dp_out, h2, w2, fh, fw);
+    edge_dp_tail_kernel<<<dim3((fh * fw + 255) / 256, P), 256, 0, st>>>(elog, dlog, edge_out, dp_out, h2, w2, fh, fw);
     IRN_LAUNCH_CHECK("edge_dp_tail_kernel");
     return kOk;
 }

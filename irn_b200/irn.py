@@ -36,25 +36,33 @@ class EdgeDisplacement(IrnParams):
             self._plan = _Plan(h, device)
         return self._plan
 
-    def forward(self, x):
+    def forward_batch(self, x):
+        """x cuda fp32 [2P,3,H,W] -> (edge [P,1,fh,fw], dp [P,2,fh,fw])."""
         _lib.require_cuda(x)
-        if x.dim() != 4 or tuple(x.shape[:2]) != (2, 3):
-            raise _lib.IrnError("EdgeDisplacement expects [2,3,H,W] (image, flipped image), got %s" % (tuple(x.shape),))
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[0] % 2:
+            raise _lib.IrnError("EdgeDisplacement expects [2P,3,H,W] (image, flipped image) pairs, got %s" % (tuple(x.shape),))
         if self.stride != 4:
             raise _lib.IrnError("EdgeDisplacement: only stride=4 (the reference default) is built")
         x = x.contiguous().float()
-        H, W = int(x.shape[2]), int(x.shape[3])
+        P, H, W = int(x.shape[0]) // 2, int(x.shape[2]), int(x.shape[3])
         L = _lib.lib()
         plan = self._get_plan(x.device)
         fh, fw = (H - 1) // 4 + 1, (W - 1) // 4 + 1
-        edge = torch.empty((1, fh, fw), dtype=torch.float32, device=x.device)
-        dp = torch.empty((2, fh, fw), dtype=torch.float32, device=x.device)
-        need = L.irn_edge_displacement_workspace_bytes(H, W, int(self.crop_size))
+        edge = torch.empty((P, 1, fh, fw), dtype=torch.float32, device=x.device)
+        dp = torch.empty((P, 2, fh, fw), dtype=torch.float32, device=x.device)
+        need = L.irn_edge_displacement_workspace_bytes(P, H, W, int(self.crop_size))
         if need == 0:
             raise _lib.IrnError("EdgeDisplacement: image %dx%d exceeds crop_size %d" % (H, W, self.crop_size))
         ws = _workspace(need, x.device)
         with torch.cuda.device(x.device):
-            rc = L.irn_edge_displacement_forward(plan.handle, _lib.ptr(x), H, W, int(self.crop_size), _lib.ptr(edge), _lib.ptr(dp),
+            rc = L.irn_edge_displacement_forward(plan.handle, _lib.ptr(x), P, H, W, int(self.crop_size), _lib.ptr(edge), _lib.ptr(dp),
                                                  _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
         _lib.check(rc, "irn_edge_displacement_forward")
         return edge, dp
+
+    def forward(self, x):
+        """Reference signature (net/resnet50_irn.py:223-234): [2,3,H,W] -> (edge [1,h,w], dp [2,h,w])."""
+        if x.dim() != 4 or tuple(x.shape[:2]) != (2, 3):
+            raise _lib.IrnError("EdgeDisplacement expects [2,3,H,W] (image, flipped image), got %s" % (tuple(x.shape),))
+        e, d = self.forward_batch(x)
+        return e[0], d[0]

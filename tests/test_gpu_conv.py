@@ -1,0 +1,48 @@
+"""The convolution kernels (SIMT fp32 and tcgen05 3xTF32) against a plain torch fp32 reference of the same
+op (F.conv2d + batch_norm on the GPU with TF32 disabled)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from irn_b200.ops import Conv2d
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # cin, cout, k, stride, pad, B, H, W
+    (64, 256, 1, 1, 0, 2, 40, 48),
+    (64, 64, 3, 1, 1, 2, 37, 53),      # ragged tiles
+    (128, 128, 3, 2, 1, 2, 64, 64),
+    (256, 512, 1, 2, 0, 2, 33, 47),
+    (512, 128, 1, 1, 0, 3, 16, 16),
+    (3, 64, 7, 2, 3, 2, 64, 80),       # stem: SIMT only
+    (2048, 32, 1, 1, 0, 2, 8, 8),      # edge head: SIMT only
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_vs_torch(cuda_dev, case):
+    cin, cout, k, stride, pad, B, H, W = case
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(cin * 7 + cout + k)
+    w = torch.randn((cout, cin, k, k), generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    bn = [1 + 0.1 * torch.randn(cout, generator=g), 0.05 * torch.randn(cout, generator=g), 0.1 * torch.randn(cout, generator=g),
+          1 + 0.2 * torch.rand(cout, generator=g)]
+    x = torch.randn((B, cin, H, W), generator=g)
+    conv = Conv2d(w.numpy(), [t.numpy() for t in bn], stride, pad)
+    xd = x.to(cuda_dev)
+    ref = F.conv2d(xd.double(), w.to(cuda_dev).double(), stride=stride, padding=pad)
+    ref = F.batch_norm(ref, bn[2].to(cuda_dev).double(), bn[3].to(cuda_dev).double(), bn[0].to(cuda_dev).double(), bn[1].to(cuda_dev).double(),
+                       training=False, eps=1e-5)
+    res = torch.randn(ref.shape, generator=g).to(cuda_dev)
+    ref = F.relu(ref + res.double()).float().permute(0, 2, 3, 1).contiguous()
+    x_nhwc = xd.permute(0, 2, 3, 1).contiguous()
+    res_nhwc = res.permute(0, 2, 3, 1).contiguous()
+    y0 = conv(x_nhwc, res_nhwc, relu=True, mode=0)
+    scale = ref.abs().max().item()
+    assert (y0 - ref).abs().max().item() / scale < 2e-6, "SIMT fp32"
+    if cin % 32 == 0 and cout % 64 == 0 and k in (1, 3):
+        y1 = conv(x_nhwc, res_nhwc, relu=True, mode=1)
+        err = (y1 - ref).abs().max().item() / scale
+        assert err < 5e-6, "tcgen05 3xTF32 rel err %g" % err
