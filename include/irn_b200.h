@@ -163,6 +163,31 @@ int irn_cam_merge(const float* const* cams, const int* hs, const int* ws, int n_
                   const int32_t* keys_dev, int K, float* strided_out, float* highres_out,
                   void* scratch, irn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * P1-P4  instance path.  Replaces step/make_ins_seg_labels.py:18-105.
+ *
+ * irn_find_centroids      P1 find_centroids_with_refinement (:18-56): dp fp32 [2,h,w] -> int32 [2,h,w] (y,x),
+ *                         bit-exact with the numpy evaluation order (float64 update, float32 state).
+ * irn_connected_components 4-connected components of equal non-zero values (skimage.measure.label(connectivity=1,
+ *                         background=0) up to numbering): labels = 0 or 1 + smallest linear index of the component,
+ *                         so ascending label order = raster order of first pixels.  scratch >= h*w*4 bytes.
+ * irn_cluster_centroids   P2 cluster_centroids (:58-75) + compress_range: instance_map int32 [h,w] in 0..I-1
+ *                         (one_hot(instance_map) is the reference's bool [I,h,w]), I -> *n_instances_dev.
+ *                         scratch >= irn_cluster_scratch_bytes(h,w).
+ * irn_instance_seeds      P3 separte_score_by_mask (:77-80): out[k*I+i] = cams[k] * (instance_map == i).
+ * irn_segment_stats       P4 detect_instance (:82-105) statistics: per segment label l: area[l], max_bits[l] =
+ *                         float bits of max(scores[index-1]) over the segment; arrays int32 [H*W+1].
+ */
+int irn_find_centroids(const float* dp, int32_t* centroids, int h, int w, int iterations, irn_stream_t stream);
+int irn_connected_components(const int32_t* values, int32_t* labels, int h, int w, void* scratch, irn_stream_t stream);
+size_t irn_cluster_scratch_bytes(int h, int w);
+int irn_cluster_centroids(const float* dp, const int32_t* centroids, float thres, int32_t* instance_map,
+                          int32_t* n_instances_dev, int h, int w, void* scratch, irn_stream_t stream);
+int irn_instance_seeds(const float* cams, const int32_t* instance_map, int K, int I, int h, int w, float* out,
+                       irn_stream_t stream);
+int irn_segment_stats(const int32_t* labels, const int32_t* index, const float* scores, int H, int W,
+                      int32_t* area, int32_t* max_bits, irn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,12 +80,26 @@ __device__ __forceinline__ float rna_tf32(float x) {
     return __uint_as_float(r);
 }
 
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     unsigned char* smem = tc_smem_raw;   // dynamic smem base is 1024-aligned by the attribute; checked below
     constexpr int kStageBytes = 2 * 16384 + 2 * BN * 128;
+    constexpr int kTmemCols = BN == 128 ? 512 : 256;   // three BN-column fp32 accumulators, power-of-two allocation
     uint64_t* bars = (uint64_t*)(smem + kTcStages * kStageBytes);
     uint64_t* full = bars;                    // [S] TMA landed
     uint64_t* split = bars + kTcStages;       // [S] A_hi / A_lo written
@@ -114,7 +128,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         fence_mbar_init();
     }
     if (warp == 1) {   // TMEM allocation: whole warp, BN fp32 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -153,9 +167,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 for (int k4 = 0; k4 < 4; ++k4) {   // UMMA_K = 8 tf32 = 32 bytes inside the 128-byte swizzle atom
                     const uint64_t da_hi = tc_smem_desc(a_hi + k4 * 32), da_lo = tc_smem_desc(a_lo + k4 * 32);
                     const uint64_t db_hi = tc_smem_desc(b_hi + k4 * 32), db_lo = tc_smem_desc(b_lo + k4 * 32);
-                    tc_mma_tf32(tmem_base, da_lo, db_hi, idesc, (kb | k4) != 0);   // small terms first
-                    tc_mma_tf32(tmem_base, da_hi, db_lo, idesc, 1);
-                    tc_mma_tf32(tmem_base, da_hi, db_hi, idesc, 1);
+                    // The tensor core's fp32 accumulation truncates: its error grows with the number of accumulation
+                    // steps into one accumulator (measured ~7e-6 rel. at K=1152 with a single accumulator).  So the
+                    // large hi*hi terms alternate between two accumulators (even / odd k-blocks) and the small
+                    // cross terms get a third; the epilogue adds the three in IEEE fp32.
+                    tc_mma_tf32(tmem_base + (uint32_t)((kb & 1) * BN), da_hi, db_hi, idesc, (kb >= 2 || k4 != 0) ? 1u : 0u);
+                    tc_mma_tf32(tmem_base + 2u * BN, da_lo, db_hi, idesc, (kb | k4) != 0);
+                    tc_mma_tf32(tmem_base + 2u * BN, da_hi, db_lo, idesc, 1);
                 }
                 tc_commit(&empty[s]);      // arrives when the MMAs above have finished reading the stage
             }
@@ -194,19 +212,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         const float* resp = args.residual ? args.residual + pix * args.Cout + n0 : nullptr;
 #pragma unroll 1
         for (int cc = 0; cc < BN / 32; ++cc) {
-            uint32_t v[32];
+            uint32_t v[32], u[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr)
-                : "memory");
+            tc_ld32(taddr, v);
+            tc_ld32(taddr + 2u * BN, u);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (KB >= 2) {   // the odd-k-block accumulator exists only when there is more than one k-block
+                uint32_t t2[32];
+                tc_ld32(taddr + (uint32_t)BN, t2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t2[j]));
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
             if (valid) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -232,7 +251,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     }
 }
 
