@@ -84,8 +84,16 @@ int irn_random_walk_variant(const float* x, const float* edge, float* out, int n
                             int n_iter, void* workspace, size_t workspace_bytes, int variant,
                             irn_stream_t stream);
 
-/* Number of kernels the last API call on this thread launched (bench.py's gpu_launches). */
+/* Number of kernels the last API call on this thread launched; irn_total_launch_count: since process start
+ * (bench.py's gpu_launches). */
 int irn_rw_last_launch_count(void);
+long long irn_total_launch_count(void);
+
+/* Device timing of the walk's step kernels for bench.py's roofline: when enabled, CUDA events are recorded on the
+ * caller's stream around the n_iter step launches; irn_rw_last_step_ms waits for the last timed walk and returns
+ * its mean step-kernel duration. */
+int irn_rw_set_timing(int enable);
+int irn_rw_last_step_ms(float* ms_per_step, int* n_steps);
 
 /* ------------------------------------------------------------------------------------
  * S1  label map.  Replaces step/make_sem_seg_labels.py:43-49 (and the same tail at

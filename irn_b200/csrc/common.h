@@ -13,6 +13,7 @@ enum { kOk = 0, kBadArg = -1, kCudaError = -2, kWorkspace = -3, kUnsupported = -
 char* last_error_buf();             // thread-local, 512 bytes
 int fail(int code, const char* fmt, ...);
 int& launch_counter();              // thread-local count of kernels launched by the last API call
+long long& total_launch_counter();  // thread-local, never reset: bench.py's gpu_launches
 
 inline int check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return kOk;
@@ -28,6 +29,7 @@ inline int check_cuda(cudaError_t e, const char* what) {
 #define IRN_LAUNCH_CHECK(name)                                    \
     do {                                                          \
         ::irn::launch_counter()++;                                \
+        ::irn::total_launch_counter()++;                          \
         int _rc = ::irn::check_cuda(cudaGetLastError(), name);    \
         if (_rc != 0) return _rc;                                 \
     } while (0)

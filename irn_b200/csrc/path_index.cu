@@ -14,6 +14,8 @@ static thread_local char g_err[512];
 static thread_local int g_launches = 0;
 char* last_error_buf() { return g_err; }
 int& launch_counter() { return g_launches; }
+static thread_local long long g_total_launches = 0;
+long long& total_launch_counter() { return g_total_launches; }
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -77,6 +79,7 @@ using namespace irn;
 
 extern "C" const char* irn_last_error(void) { return last_error_buf(); }
 extern "C" int irn_version(void) { return 100; }
+extern "C" long long irn_total_launch_count(void) { return total_launch_counter(); }
 
 extern "C" int irn_path_index_shape(int radius, int* n_dst, int* n_groups, int* group_len, int* group_paths) {
     if (radius < 2 || radius > 64) return fail(kBadArg, "irn_path_index_shape: radius %d out of range [2,64]", radius);

@@ -423,6 +423,12 @@ static int launch_tma_steps(const RwWorkspace& ws, int n_img, int totc, int h, i
     return kOk;
 }
 
+// Optional device timing of the step kernels (bench.py roofline): events recorded on the caller's stream around the
+// n_iter step launches of the most recent walk on this thread.
+static thread_local bool g_rw_timing = false;
+static thread_local cudaEvent_t g_rw_ev[2] = {nullptr, nullptr};
+static thread_local int g_rw_timed_iters = 0;
+
 static int walk_impl(const float* x, const float* edge, float* out, int n_img, const int32_t* chan_offsets, int h, int w,
                      int radius, double beta, int n_iter, void* workspace, size_t workspace_bytes, int variant,
                      cudaStream_t stream) {
@@ -465,6 +471,13 @@ static int walk_impl(const float* x, const float* edge, float* out, int n_img, c
     rw_init_kernel<<<pgrid, 256, 0, stream>>>(x, edge, ws.y[0], ws.chan_off, h, w, pitch);
     IRN_LAUNCH_CHECK("rw_init_kernel");
 
+    if (g_rw_timing) {
+        if (!g_rw_ev[0]) {
+            IRN_CUDA(cudaEventCreate(&g_rw_ev[0]));
+            IRN_CUDA(cudaEventCreate(&g_rw_ev[1]));
+        }
+        IRN_CUDA(cudaEventRecord(g_rw_ev[0], stream));
+    }
     if (radius == 5 && variant != 1) {
         const int ch = max_c >= 4 ? 4 : max_c;
         if (ch == 1) rc = launch_tma_steps<1>(ws, n_img, totc, h, w, n_iter, stream);
@@ -477,6 +490,10 @@ static int walk_impl(const float* x, const float* edge, float* out, int n_img, c
             rw_step_generic_kernel<<<pgrid, 256, 0, stream>>>(ws.W, ws.inv_s, ws.y[it & 1], ws.y[(it + 1) & 1], ws.chan_off, h, w, pitch);
             IRN_LAUNCH_CHECK("rw_step_generic_kernel");
         }
+    }
+    if (g_rw_timing) {
+        IRN_CUDA(cudaEventRecord(g_rw_ev[1], stream));
+        g_rw_timed_iters = n_iter;
     }
     {
         const size_t n = (size_t)totc * hw;
@@ -513,6 +530,22 @@ extern "C" size_t irn_rw_workspace_bytes(int n_img, int h, int w, int total_chan
 }
 
 extern "C" int irn_rw_last_launch_count(void) { return launch_counter(); }
+
+extern "C" int irn_rw_set_timing(int enable) {
+    g_rw_timing = enable != 0;
+    return kOk;
+}
+
+// Average duration (ms) of one step-kernel launch of the last timed walk on this thread; blocks until it finished.
+extern "C" int irn_rw_last_step_ms(float* ms_per_step, int* n_steps) {
+    if (!ms_per_step || !g_rw_ev[0] || g_rw_timed_iters <= 0) return fail(kBadArg, "irn_rw_last_step_ms: no timed walk (call irn_rw_set_timing(1) first)");
+    IRN_CUDA(cudaEventSynchronize(g_rw_ev[1]));
+    float ms = 0.f;
+    IRN_CUDA(cudaEventElapsedTime(&ms, g_rw_ev[0], g_rw_ev[1]));
+    *ms_per_step = ms / (float)g_rw_timed_iters;
+    if (n_steps) *n_steps = g_rw_timed_iters;
+    return kOk;
+}
 
 extern "C" int irn_random_walk(const float* x, const float* edge, float* out, int n_img, const int32_t* chan_offsets,
                                int h, int w, int radius, double beta, int n_iter, void* workspace,

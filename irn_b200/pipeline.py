@@ -1,0 +1,85 @@
+"""Batched pseudo-label pipeline: the reference's make_cam -> make_sem_seg_labels chain
+(step/make_cam.py:28-56, step/make_sem_seg_labels.py:28-51) for a batch of equally-sized images, kept on the
+device end to end (the reference round-trips every image through a .npy file and one-image kernels).
+
+    multi-scale CAM (C2-C4) -> EdgeDisplacement (I1/I2) -> random walk (R1-R6) -> label map (S1)
+"""
+import numpy as np
+import torch
+
+from . import cam_ops, indexing
+from .voc12 import dataloader as voc_data
+
+
+def preprocess_batch(images_u8, scales=(1.0, 0.5, 1.5, 2.0), pin=True):
+    """C1 on the host (voc12/dataloader.py:185-205): list of uint8 [H,W,3] of one size -> list over scales of
+    float32 tensors [2N,3,h_s,w_s] (image, flipped image interleaved), pinned for async H2D."""
+    per_scale = [[] for _ in scales]
+    for img in images_u8:
+        ms = voc_data.multi_scale_flip(img, scales)
+        ms = ms if isinstance(ms, list) else [ms]
+        for s, a in enumerate(ms):
+            per_scale[s].append(a)
+    out = []
+    for lst in per_scale:
+        t = torch.from_numpy(np.ascontiguousarray(np.concatenate(lst, 0)))
+        out.append(t.pin_memory() if pin and torch.cuda.is_available() else t)
+    return out
+
+
+class PseudoLabelPipeline:
+    def __init__(self, cam_model, irn_model, device, scales=(1.0, 0.5, 1.5, 2.0), beta=10, exp_times=8, bg_thres=0.25,
+                 cam_sub_batch=8, rw_sub_batch=24):
+        self.cam, self.irn, self.device = cam_model, irn_model, device
+        self.scales, self.beta, self.exp_times, self.bg = scales, beta, exp_times, bg_thres
+        self.cam_sub, self.rw_sub = cam_sub_batch, rw_sub_batch
+        if 1.0 not in scales:
+            raise ValueError("the IRNet pass uses the scale-1.0 input (step/make_sem_seg_labels.py:64-66)")
+
+    @torch.no_grad()
+    def run(self, inputs, labels, size, want_highres=True):
+        """inputs: list over scales of [2N,3,h_s,w_s] fp32 (cuda, or pinned host -> copied here);
+        labels: [N,20] multi-hot; size=(H,W).  Returns dict with 'labels' uint8 cuda [N,H,W], 'keys' list,
+        'cams' list of cuda [K_i,h4,w4] and 'high_res' list (or None)."""
+        dev = self.device
+        xs = [x.to(dev, non_blocking=True) if not x.is_cuda else x for x in inputs]
+        N = xs[0].shape[0] // 2
+        # ---- C2/C3: CAM forward per scale, in sub-batches of image pairs
+        cams = []
+        for x in xs:
+            outs = [self.cam.forward_batch(x[2 * i:2 * min(i + self.cam_sub, N)]) for i in range(0, N, self.cam_sub)]
+            cams.append(torch.cat(outs, 0))
+        # ---- C4: merge + normalise per image (classes present differ per image)
+        keys, strided, highres = [], [], []
+        for i in range(N):
+            k, lo, hi = cam_ops.merge_cams([c[i] for c in cams], size, labels[i])
+            keys.append(k.numpy())
+            strided.append(lo)
+            highres.append(hi if want_highres else None)
+        # ---- I1/I2: edge + displacement
+        x1 = xs[self.scales.index(1.0)]
+        edges = []
+        for i in range(0, N, self.cam_sub):
+            e, _ = self.irn.forward_batch(x1[2 * i:2 * min(i + self.cam_sub, N)])
+            edges.append(e[:, 0])
+        edges = torch.cat(edges, 0)
+        # ---- R1-R6: batched walk (sub-batches sized so the weights stay L2-resident)
+        counts = [int(s.shape[0]) for s in strided]
+        rws = []
+        for i in range(0, N, self.rw_sub):
+            j = min(i + self.rw_sub, N)
+            offs = np.concatenate([[0], np.cumsum(counts[i:j])])
+            seeds = torch.cat(strided[i:j], 0)
+            rws.append(indexing.random_walk_batch(seeds, edges[i:j], offs, 5, self.beta, 2 ** self.exp_times))
+        rw = torch.cat(rws, 0)
+        # ---- S1: label maps
+        out = torch.empty((N, size[0], size[1]), dtype=torch.uint8, device=dev)
+        o = 0
+        for i in range(N):
+            if counts[i]:
+                lab, _, _ = indexing.rw_labels(rw[o:o + counts[i]], keys[i], size, self.bg)
+                out[i] = lab
+            else:
+                out[i].zero_()
+            o += counts[i]
+        return {"labels": out, "keys": keys, "cams": strided, "high_res": highres if want_highres else None, "edge": edges}
