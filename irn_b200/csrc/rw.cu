@@ -365,6 +365,151 @@ rw_step_tma_kernel(const __grid_constant__ RwMaps maps, const double* __restrict
     }
 }
 
+// ---------------------------------------------------------------- persistent ring step kernel (radius 5, production)
+// Same arithmetic as rw_step_tma_kernel, restructured so that TMA latency is never exposed: one persistent CTA per SM
+// walks tiles b, b+G, b+2G, ...; warp 4 is a TMA producer that runs ahead through a ring of kRingW weight-class buffers and
+// two state-tile buffers (full/empty mbarriers, no __syncthreads in the loop), warps 0-3 consume.  ~200 KB of loads stay
+// in flight per SM instead of ~60 KB.
+template <int CH>
+struct RingCfg {
+    static constexpr int kYBytes = CH * kYH * kSW * (int)sizeof(double);
+    static constexpr int kWBytes = kWBufFloats * (int)sizeof(float);
+    static constexpr int kStagesW = (227 * 1024 - 2 * kYBytes - 512) / kWBytes > 8 ? 8 : (227 * 1024 - 2 * kYBytes - 512) / kWBytes;
+    static constexpr int kSmem = 2 * kYBytes + kStagesW * kWBytes + 512;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(kTX* kWarps + 32, 1)
+rw_step_ring_kernel(const __grid_constant__ RwMaps maps, const double* __restrict__ inv_s, double* __restrict__ yout,
+                    const int* __restrict__ chan_off, int h, int w, int pitch, int n_img, int tiles_x, int tiles_y) {
+    using Cfg = RingCfg<CH>;
+    constexpr int NW = Cfg::kStagesW;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* s_y = (double*)smem_raw;                                   // [2][CH][kYH][kSW]
+    float* s_w = (float*)(smem_raw + 2 * Cfg::kYBytes);               // [NW][<=9][kWH][kSW]
+    uint64_t* bars = (uint64_t*)(smem_raw + 2 * Cfg::kYBytes + NW * Cfg::kWBytes);
+    uint64_t* fullY = bars;            // [2]
+    uint64_t* emptyY = bars + 2;       // [2]
+    uint64_t* fullW = bars + 4;        // [NW]
+    uint64_t* emptyW = bars + 4 + NW;  // [NW]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&fullY[i], 1);
+            mbar_init(&emptyY[i], kWarps);
+        }
+        for (int i = 0; i < NW; ++i) {
+            mbar_init(&fullW[i], 1);
+            mbar_init(&emptyW[i], kWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int tiles = tiles_x * tiles_y;
+    const int n_items = n_img * tiles;
+    const size_t plane_sz = (size_t)h * pitch;
+
+    if (warp == kWarps) {
+        // ------------------------------------------------ producer
+        if (lane == 0) {
+            uint32_t ny = 0, nw = 0;   // sub-items / weight chunks issued so far
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int img = item / tiles, t = item % tiles;
+                const int x0 = (t % tiles_x) * kTX, y0 = (t / tiles_x) * kTY;
+                const int c_begin = chan_off[img], c_end = chan_off[img + 1];
+                for (int c0 = c_begin; c0 < c_end; c0 += CH) {
+                    const uint32_t ys = ny & 1;
+                    mbar_wait(&emptyY[ys], ((ny >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&fullY[ys], (uint32_t)Cfg::kYBytes);
+                    tma_load_3d((unsigned char*)s_y + ys * Cfg::kYBytes, &maps.y, &fullY[ys], x0 - kR, y0 - kR, c0);
+                    ++ny;
+#pragma unroll
+                    for (int cls = 0; cls < 5; ++cls) {
+                        const uint32_t slot = nw % NW;
+                        mbar_wait(&emptyW[slot], ((nw / NW) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&fullW[slot], (uint32_t)((cls_base5(cls + 1) - cls_base5(cls)) * kWH * kSW * sizeof(float)));
+                        tma_load_3d(s_w + slot * kWBufFloats, &maps.w[cls], &fullW[slot], x0 - kR, y0 - kR, img * 34 + cls_base5(cls));
+                        ++nw;
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------- consumers (warps 0..3)
+    const int ty0 = warp * kPY;
+    uint32_t ny = 0, nw = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int img = item / tiles, t = item % tiles;
+        const int x0 = (t % tiles_x) * kTX, y0 = (t / tiles_x) * kTY;
+        const int x = x0 + lane, yb = y0 + ty0;
+        const int c_begin = chan_off[img], c_end = chan_off[img + 1];
+        for (int c0 = c_begin; c0 < c_end; c0 += CH) {
+            const uint32_t ys = ny & 1;
+            const double* sy = (const double*)((const unsigned char*)s_y + ys * Cfg::kYBytes);
+            mbar_wait(&fullY[ys], (ny >> 1) & 1);
+            ++ny;
+            double acc[kPY][CH];
+#pragma unroll
+            for (int j = 0; j < kPY; ++j)
+#pragma unroll
+                for (int c = 0; c < CH; ++c) acc[j][c] = sy[(c * kYH + ty0 + j + kR) * kSW + lane + kR];   // diagonal weight 1
+
+            static_for<0, 5>([&](auto CLS) {
+                constexpr int cls = decltype(CLS)::value;
+                const uint32_t slot = nw % NW;
+                const float* wb = s_w + slot * kWBufFloats;
+                mbar_wait(&fullW[slot], (nw / NW) & 1);
+                ++nw;
+                static_for<0, (cls == 0 ? 1 : 2)>([&](auto SGN) {
+                    constexpr int dxc = decltype(SGN)::value == 0 ? cls : -cls;
+                    static_for<-kR, kPY + kR>([&](auto RR) {
+                        constexpr int r = decltype(RR)::value;
+                        double v[CH];
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) v[c] = sy[(c * kYH + ty0 + r + kR) * kSW + lane + dxc + kR];
+                        static_for<0, kPY>([&](auto JJ) {
+                            constexpr int j = decltype(JJ)::value;
+                            constexpr int dy = r - j;
+                            constexpr int kf = plane5(dy, dxc);
+                            constexpr int kb = plane5(-dy, -dxc);
+                            if constexpr (kf >= 0) {
+                                const double wv = widen_weight(wb[((kf - cls_base5(cls)) * kWH + ty0 + j + kR) * kSW + lane + kR]);
+#pragma unroll
+                                for (int c = 0; c < CH; ++c) acc[j][c] = fma(wv, v[c], acc[j][c]);
+                            } else if constexpr (kb >= 0) {
+                                const double wv = widen_weight(wb[((kb - cls_base5(cls)) * kWH + ty0 + r + kR) * kSW + lane + dxc + kR]);
+#pragma unroll
+                                for (int c = 0; c < CH; ++c) acc[j][c] = fma(wv, v[c], acc[j][c]);
+                            }
+                        });
+                    });
+                });
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&emptyW[slot]);   // this warp is done with the weight buffer
+            });
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyY[ys]);          // ... and with the state tile
+
+            if (x < w) {
+#pragma unroll
+                for (int j = 0; j < kPY; ++j) {
+                    if (yb + j < h) {
+                        const double is = inv_s[(size_t)img * plane_sz + (size_t)(yb + j) * pitch + x];
+#pragma unroll
+                        for (int c = 0; c < CH; ++c)
+                            if (c0 + c < c_end) yout[(size_t)(c0 + c) * plane_sz + (size_t)(yb + j) * pitch + x] = acc[j][c] * is;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- workspace carving
 struct RwWorkspace {
     float* W;
@@ -396,7 +541,7 @@ static RwWorkspace carve(void* base, int n_img, int h, int w, int totc, int n_ds
 }
 
 template <int CH>
-static int launch_tma_steps(const RwWorkspace& ws, int n_img, int totc, int h, int w, int n_iter, cudaStream_t stream) {
+static int launch_tma_steps(const RwWorkspace& ws, int n_img, int totc, int h, int w, int n_iter, int variant, cudaStream_t stream) {
     const int pitch = ws.pitch;
     RwMaps maps[2];
     for (int b = 0; b < 2; ++b) {
@@ -413,12 +558,28 @@ static int launch_tma_steps(const RwWorkspace& ws, int n_img, int totc, int h, i
         int rc = make_tensor_map(&maps[b].y, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ws.y[b], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc) return rc;
     }
-    const size_t smem = rw_tma_smem_bytes(CH);
-    IRN_CUDA(cudaFuncSetAttribute(rw_step_tma_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(((w + kTX - 1) / kTX) * ((h + kTY - 1) / kTY), n_img);
+    const int tiles_x = (w + kTX - 1) / kTX, tiles_y = (h + kTY - 1) / kTY;
+    if (variant == 2) {   // previous two-buffer kernel, kept for A/B measurements
+        const size_t smem = rw_tma_smem_bytes(CH);
+        IRN_CUDA(cudaFuncSetAttribute(rw_step_tma_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(tiles_x * tiles_y, n_img);
+        for (int it = 0; it < n_iter; ++it) {
+            rw_step_tma_kernel<CH><<<grid, kTX * kWarps, smem, stream>>>(maps[it & 1], ws.inv_s, ws.y[(it + 1) & 1], ws.chan_off, h, w, pitch);
+            IRN_LAUNCH_CHECK("rw_step_tma_kernel");
+        }
+        return kOk;
+    }
+    int dev = 0, n_sm = 0;
+    IRN_CUDA(cudaGetDevice(&dev));
+    IRN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    const int smem = RingCfg<CH>::kSmem;
+    IRN_CUDA(cudaFuncSetAttribute(rw_step_ring_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int n_items = tiles_x * tiles_y * n_img;
+    const int grid = n_items < n_sm ? n_items : n_sm;   // one persistent CTA per SM
     for (int it = 0; it < n_iter; ++it) {
-        rw_step_tma_kernel<CH><<<grid, kTX * kWarps, smem, stream>>>(maps[it & 1], ws.inv_s, ws.y[(it + 1) & 1], ws.chan_off, h, w, pitch);
-        IRN_LAUNCH_CHECK("rw_step_tma_kernel");
+        rw_step_ring_kernel<CH><<<grid, kTX * kWarps + 32, smem, stream>>>(maps[it & 1], ws.inv_s, ws.y[(it + 1) & 1], ws.chan_off, h, w, pitch,
+                                                                            n_img, tiles_x, tiles_y);
+        IRN_LAUNCH_CHECK("rw_step_ring_kernel");
     }
     return kOk;
 }
@@ -480,10 +641,10 @@ static int walk_impl(const float* x, const float* edge, float* out, int n_img, c
     }
     if (radius == 5 && variant != 1) {
         const int ch = max_c >= 4 ? 4 : max_c;
-        if (ch == 1) rc = launch_tma_steps<1>(ws, n_img, totc, h, w, n_iter, stream);
-        else if (ch == 2) rc = launch_tma_steps<2>(ws, n_img, totc, h, w, n_iter, stream);
-        else if (ch == 3) rc = launch_tma_steps<3>(ws, n_img, totc, h, w, n_iter, stream);
-        else rc = launch_tma_steps<4>(ws, n_img, totc, h, w, n_iter, stream);
+        if (ch == 1) rc = launch_tma_steps<1>(ws, n_img, totc, h, w, n_iter, variant, stream);
+        else if (ch == 2) rc = launch_tma_steps<2>(ws, n_img, totc, h, w, n_iter, variant, stream);
+        else if (ch == 3) rc = launch_tma_steps<3>(ws, n_img, totc, h, w, n_iter, variant, stream);
+        else rc = launch_tma_steps<4>(ws, n_img, totc, h, w, n_iter, variant, stream);
         if (rc) return rc;
     } else {
         for (int it = 0; it < n_iter; ++it) {
@@ -553,7 +714,8 @@ extern "C" int irn_random_walk(const float* x, const float* edge, float* out, in
     return walk_impl(x, edge, out, n_img, chan_offsets, h, w, radius, beta, n_iter, workspace, workspace_bytes, 0, (cudaStream_t)stream);
 }
 
-// variant: 0 = production path (TMA step kernel for radius 5), 1 = generic bounds-checked kernel (validation)
+// variant: 0 = production path (persistent TMA-ring step kernel, radius 5), 1 = generic bounds-checked kernel (validation),
+// 2 = the earlier two-buffer TMA kernel (A/B measurements)
 extern "C" int irn_random_walk_variant(const float* x, const float* edge, float* out, int n_img, const int32_t* chan_offsets,
                                        int h, int w, int radius, double beta, int n_iter, void* workspace,
                                        size_t workspace_bytes, int variant, irn_stream_t stream) {
