@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_threads():
-    return min(os.cpu_count(), int(os.environ.get("IRN_CPU_THREADS", "64")))
+    return min(os.cpu_count(), int(os.environ.get("IRN_CPU_THREADS", "32"))   # measured on the B200 host: 128 torch threads are 50x slower than 16-32)
 
 
 def dense_walk_sample(cam, edge):
@@ -198,7 +198,7 @@ def main():
     cam.cuda(dev), irn.cuda(dev)
     for m in (cam, irn):
         _lib.check(L.irn_net_set_conv_mode(m._get_plan(dev).handle, a.conv_mode))
-    pipe = PseudoLabelPipeline(cam, irn, dev, SCALES, rw_sub_batch=32)
+    pipe = PseudoLabelPipeline(cam, irn, dev, SCALES, rw_sub_batch=24)
 
     # ---- synthetic inputs: rank r takes images r, r+N, ... of the global list (misc/torchutils.py:66-68)
     B = a.batch

@@ -78,7 +78,7 @@ int irn_random_walk(const float* x, const float* edge, float* out, int n_img,
 
 /* Same, selecting the step kernel: variant 0 = production (TMA-staged register-window kernel,
  * radius 5), 1 = generic bounds-checked kernel (any radius 2..10; validation / fallback for
- * radii the reference's hot path never uses). */
+ * radii the reference's hot path never uses), 3 = persistent TMA-ring experiment (radius 5). */
 int irn_random_walk_variant(const float* x, const float* edge, float* out, int n_img,
                             const int32_t* chan_offsets, int h, int w, int radius, double beta,
                             int n_iter, void* workspace, size_t workspace_bytes, int variant,

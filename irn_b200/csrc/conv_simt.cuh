@@ -151,6 +151,27 @@ __global__ void nchw_to_nhwc_pad_kernel(const float* __restrict__ in, float* __r
     out[i] = (y < H && x < W) ? in[(((size_t)b * C + c) * H + y) * W + x] : 0.f;
 }
 
+// NCHW fp32 [B,3,H,W] -> zero-haloed NHWC4 [B, Hin+6, Win+8, 4] for the tensor-core stem: pixel (y,x) lands at
+// (y+3, x+3), channel 3 and everything outside the real HxW image is 0 (conv zero padding + IRNet's crop padding).
+__global__ void nchw_to_nhwc4_halo_kernel(const float* __restrict__ in, float4* __restrict__ out, int B, int H, int W, int Hp, int Wp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)B * Hp * Wp;
+    if (i >= total) return;
+    const int px = (int)(i % Wp);
+    const int py = (int)((i / Wp) % Hp);
+    const int b = (int)(i / ((size_t)Wp * Hp));
+    const int x = px - 3, y = py - 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x >= 0 && x < W && y >= 0 && y < H) {
+        const size_t plane = (size_t)H * W;
+        const float* p = in + (size_t)b * 3 * plane + (size_t)y * W + x;
+        v.x = p[0];
+        v.y = p[plane];
+        v.z = p[2 * plane];
+    }
+    out[i] = v;
+}
+
 // MaxPool2d(3, stride 2, pad 1), -inf padding (net/resnet50.py:66).  NHWC, C % 4 == 0.
 __global__ void maxpool3s2_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C, int Ho, int Wo) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,50 +254,38 @@ __global__ void cam_head_kernel(const float* __restrict__ feat, const float* __r
     }
 }
 
-// GroupNorm statistics (biased variance, eps added by the consumer): one block per (sample, group).
-// x NHWC [B,H,W,C]; stats[(b*G+g)*2 + {0,1}] = {mean, rstd}
-__global__ void gn_stats_kernel(const float* __restrict__ x, float* __restrict__ stats, int HW, int C, int G, float eps) {
-    const int b = blockIdx.x / G, g = blockIdx.x % G;
-    const int cpg = C / G;
-    const size_t n = (size_t)HW * cpg;
+// GroupNorm statistics, pass 1: per (sample, group) sum and sum of squares in fp64.  grid (slices, B), 256 threads;
+// thread t owns channel t % C of every (256/C)-th pixel of its slice, so global reads are fully coalesced; the
+// per-channel partials are folded per group through shared-memory atomics, then one atomicAdd per group per block.
+// x NHWC [B,HW,C], C in {32,64,128,256}; sums[(b*G+g)*2 + {0,1}] must be zeroed beforehand.
+__global__ void __launch_bounds__(256)
+gn_partial_kernel(const float* __restrict__ x, double* __restrict__ sums, int HW, int C, int G) {
+    __shared__ double sh[32][2];
+    const int b = blockIdx.y;
+    const int c = threadIdx.x % C, prow = threadIdx.x / C, pstep = 256 / C;
+    const int per = (HW + gridDim.x - 1) / gridDim.x;
+    const int p0 = blockIdx.x * per, p1 = min(p0 + per, HW);
+    if (threadIdx.x < 32) sh[threadIdx.x][0] = sh[threadIdx.x][1] = 0.0;
+    __syncthreads();
     double s = 0.0, ss = 0.0;
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const size_t pix = i / cpg;
-        const int c = (int)(i % cpg);
-        const double v = (double)x[((size_t)b * HW + pix) * C + g * cpg + c];
+    for (int p = p0 + prow; p < p1; p += pstep) {
+        const double v = (double)x[((size_t)b * HW + p) * C + c];
         s += v;
         ss += v * v;
     }
-    __shared__ double sh[2][32];
-    for (int o = 16; o; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        sh[0][threadIdx.x >> 5] = s;
-        sh[1][threadIdx.x >> 5] = ss;
-    }
+    const int g = c / (C / G);
+    atomicAdd(&sh[g][0], s);
+    atomicAdd(&sh[g][1], ss);
     __syncthreads();
-    if (threadIdx.x < 32) {
-        s = threadIdx.x < (blockDim.x >> 5) ? sh[0][threadIdx.x] : 0.0;
-        ss = threadIdx.x < (blockDim.x >> 5) ? sh[1][threadIdx.x] : 0.0;
-        for (int o = 16; o; o >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        }
-        if (threadIdx.x == 0) {
-            const double mean = s / (double)n;
-            double var = ss / (double)n - mean * mean;
-            var = var < 0.0 ? 0.0 : var;
-            stats[2 * blockIdx.x] = (float)mean;
-            stats[2 * blockIdx.x + 1] = (float)(1.0 / sqrt(var + (double)eps));
-        }
+    if (threadIdx.x < G) {
+        atomicAdd(&sums[(size_t)(b * G + threadIdx.x) * 2], sh[threadIdx.x][0]);
+        atomicAdd(&sums[(size_t)(b * G + threadIdx.x) * 2 + 1], sh[threadIdx.x][1]);
     }
 }
 
 // GroupNorm affine -> bilinear upsample by `up` (align_corners=False) -> ReLU, written into a channel slice
 // of a concat buffer, cropped to (Hd, Wd)   (net/resnet50_irn.py:23-93,117-131: conv -> GN -> Upsample -> ReLU).
-__global__ void gn_up_relu_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+__global__ void gn_up_relu_kernel(const float* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, float* __restrict__ dst, int B, int H, int W, int C, int G, int up,
                                   int Hd, int Wd, int Cd, int coff) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,7 +298,12 @@ __global__ void gn_up_relu_kernel(const float* __restrict__ x, const float* __re
     const int Y = (int)(r % Hd);
     const int b = (int)(r / Hd);
     const int g = c / (C / G);
-    const float mean = stats[2 * (b * G + g)], rstd = stats[2 * (b * G + g) + 1];
+    // biased variance over the (C/G)*H*W elements of the group, eps inside the sqrt (torch GroupNorm)
+    const double cnt = (double)H * W * (C / G);
+    const double mu = sums[2 * (b * G + g)] / cnt;
+    double var = sums[2 * (b * G + g) + 1] / cnt - mu * mu;
+    var = var < 0.0 ? 0.0 : var;
+    const float mean = (float)mu, rstd = (float)(1.0 / sqrt(var + 1e-5));
     const float ga = gamma[c], be = beta[c];
     const float* xb = x + (size_t)b * H * W * C + c;
     float v;

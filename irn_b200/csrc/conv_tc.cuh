@@ -36,6 +36,7 @@ struct TcArgs {
     float* out;
     int B, Ho, Wo, Cout, Cin, ksize, stride, pad, relu;
     int tiles_x, tiles_y;
+    int mode;   // 0: NHWC input, one k-block per (tap, 32-channel slice); 1: stem, NHWC4 zero-haloed input, one k-block per filter row
 };
 
 constexpr size_t tc_smem_bytes(int BN) {
@@ -115,7 +116,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     const int ox0 = tx * kTcTW, oy0 = ty * kTcTH;
     const int n0 = blockIdx.y * BN;
     const int cblocks = args.Cin / kTcBK;
-    const int KB = args.ksize * args.ksize * cblocks;
+    const int KB = args.mode == 1 ? args.ksize : args.ksize * args.ksize * cblocks;
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -148,7 +149,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 const int tap = kb / cblocks, cb = kb % cblocks;
                 const int r = tap / args.ksize, ss = tap % args.ksize;
                 mbar_arrive_expect_tx(&full[s], 16384u + 2u * BN * 128u);
-                tma_load_4d(st, &maps.a, &full[s], cb * kTcBK, ox0 * args.stride - args.pad + ss, oy0 * args.stride - args.pad + r, b);
+                if (args.mode == 1)   // stem: row kb of the 7x7 filter; the 8 px x 4 ch window of output ox starts at padded px = 2*ox
+                    tma_load_4d(st, &maps.a, &full[s], 0, ox0, oy0 * 2 + kb, b);
+                else
+                    tma_load_4d(st, &maps.a, &full[s], cb * kTcBK, ox0 * args.stride - args.pad + ss, oy0 * args.stride - args.pad + r, b);
                 tma_load_2d(st + 32768, &maps.b_hi, &full[s], kb * kTcBK, n0);
                 tma_load_2d(st + 32768 + BN * 128, &maps.b_lo, &full[s], kb * kTcBK, n0);
             }
@@ -200,16 +204,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[s]);
         }
-        // ---- epilogue
+        // ---- epilogue.  Phase 1: TMEM -> registers (thread = one tile row), sum the three accumulators, park the
+        // 32 x BN block of this warp in shared memory (the pipeline stages are idle once acc_full fired).  Phase 2: the warp
+        // walks its 32 rows with lanes across the channels, so bias / residual loads and the output stores are full
+        // 512-byte (256 for BN=64) coalesced segments instead of 32 scattered 16-byte pieces per instruction.
         mbar_wait(acc_full, 0);
         tc_fence_after();
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;          // tile row = output pixel
-        const int oy = oy0 + row / kTcTW, ox = ox0 + row % kTcTW;
-        const bool valid = oy < args.Ho && ox < args.Wo;
-        const size_t pix = ((size_t)b * args.Ho + oy) * args.Wo + ox;
-        float* outp = args.out + pix * args.Cout + n0;
-        const float* resp = args.residual ? args.residual + pix * args.Cout + n0 : nullptr;
+        constexpr int kLd = BN + 4;             // padded row stride (floats): conflict-free float4 rows
+        float* stg = reinterpret_cast<float*>(smem) + (size_t)q * 32 * kLd;
 #pragma unroll 1
         for (int cc = 0; cc < BN / 32; ++cc) {
             uint32_t v[32], u[32];
@@ -225,25 +228,38 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t2[j]));
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]); o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
-                    if (args.bias) {
-                        const float4 bi = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + cc * 32 + j));
-                        o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w;
-                    }
-                    if (resp) {
-                        const float4 rr = __ldg(reinterpret_cast<const float4*>(resp + cc * 32 + j));
-                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                    }
-                    if (args.relu) {
-                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                    }
-                    *reinterpret_cast<float4*>(outp + cc * 32 + j) = o;
+            for (int j = 0; j < 32; j += 4) {
+                float4 o;
+                o.x = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                o.y = __uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1]);
+                o.z = __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]);
+                o.w = __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3]);
+                *reinterpret_cast<float4*>(stg + lane * kLd + cc * 32 + j) = o;
+            }
+        }
+        __syncwarp();
+        constexpr int kLanesPerRow = BN / 4;            // 32 (BN=128) or 16 (BN=64)
+        constexpr int kRowsPerIter = 32 / kLanesPerRow;
+        const int sub = lane / kLanesPerRow, col = (lane % kLanesPerRow) * 4;
+        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (args.bias) bi = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + col));
+#pragma unroll 4
+        for (int r0 = 0; r0 < 32; r0 += kRowsPerIter) {
+            const int r = r0 + sub;
+            const int row = q * 32 + r;
+            const int oy = oy0 + row / kTcTW, ox = ox0 + row % kTcTW;
+            if (oy < args.Ho && ox < args.Wo) {
+                const size_t off = (((size_t)b * args.Ho + oy) * args.Wo + ox) * args.Cout + n0 + col;
+                float4 o = *reinterpret_cast<const float4*>(stg + r * kLd + col);
+                o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w;
+                if (args.residual) {
+                    const float4 rr = __ldg(reinterpret_cast<const float4*>(args.residual + off));
+                    o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
                 }
+                if (args.relu) {
+                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                }
+                *reinterpret_cast<float4*>(args.out + off) = o;
             }
         }
     }

@@ -26,6 +26,7 @@ struct Conv {
     float* w_lo = nullptr;
     int bn = 0;              // N tile (64 or 128); 0 = not eligible
     CUtensorMap map_bhi, map_blo;
+    bool stem_tc = false;    // 7x7/s2 stem repacked as 7 k-blocks of (8 taps x 4 channels) over a zero-haloed NHWC4 input
 };
 
 struct Head {            // conv1x1 (no bias) -> GroupNorm(groups) -> [upsample] -> ReLU
@@ -156,6 +157,35 @@ static int read_vec(irn_net* net, Reader& rd, size_t n, float** out) {
 static int read_trunk(irn_net* net, Reader& rd) {
     int rc = read_conv(net, rd, net->stem, 3, 64, 7, 2, 3, true);
     if (rc) return rc;
+    {   // tensor-core stem: K = 7 rows x (8 taps x 4 channels) = 224, tap 7 and channel 3 carry zero weights
+        Conv& c = net->stem;
+        std::vector<float> host((size_t)49 * 3 * 64);
+        IRN_CUDA(cudaMemcpy(host.data(), c.wt, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        const size_t K = 224;
+        std::vector<float> hi(64 * K, 0.f), lo(64 * K, 0.f);
+        for (int o = 0; o < 64; ++o)
+            for (int r = 0; r < 7; ++r)
+                for (int t = 0; t < 7; ++t)
+                    for (int ci = 0; ci < 3; ++ci) {
+                        const float v = host[((size_t)(r * 7 + t) * 3 + ci) * 64 + o];
+                        uint32_t u;
+                        std::memcpy(&u, &v, 4);
+                        uint32_t h = (u + 0x1000u) & 0xFFFFE000u;
+                        float hf;
+                        std::memcpy(&hf, &h, 4);
+                        if (!std::isfinite(hf)) hf = v;
+                        hi[(size_t)o * K + r * 32 + t * 4 + ci] = hf;
+                        lo[(size_t)o * K + r * 32 + t * 4 + ci] = v - hf;
+                    }
+        if ((rc = upload(net, hi, &c.w_hi))) return rc;
+        if ((rc = upload(net, lo, &c.w_lo))) return rc;
+        const uint64_t dims[2] = {K, 64};
+        const uint64_t strides[1] = {K * sizeof(float)};
+        const uint32_t box[2] = {(uint32_t)kTcBK, 64};
+        if ((rc = make_tensor_map(&c.map_bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tensor_map(&c.map_blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        c.stem_tc = true;
+    }
     int cin = 64;
     for (int l = 0; l < 4; ++l) {
         net->blocks[l].resize(kBlocks[l]);
@@ -208,9 +238,42 @@ static int launch_tc(const Conv& c, const float* in, int B, int H, int W, int Ho
     a.relu = relu ? 1 : 0;
     a.tiles_x = (Wo + kTcTW - 1) / kTcTW;
     a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
+    a.mode = 0;
     dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B), (unsigned)(c.cout / BN));
     conv_tc_kernel<BN><<<grid, kTcThreads, tc_smem_bytes(BN), st>>>(maps, a);
     IRN_LAUNCH_CHECK("conv_tc_kernel");
+    return kOk;
+}
+
+// Tensor-core stem: x4 = zero-haloed NHWC4 input [B, Hin+6, Win+8, 4]; out NHWC [B,Ho,Wo,64] with bias + ReLU.
+static int launch_tc_stem(const Conv& c, const float* x4, int B, int Hin, int Win, float* out, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        IRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(64)));
+        attr_set = true;
+    }
+    const int Hp = Hin + 6, Wp = Win + 8;
+    const int Ho = conv_out(Hin, 7, 2, 3), Wo = conv_out(Win, 7, 2, 3);
+    TcMaps maps;
+    maps.b_hi = c.map_bhi;
+    maps.b_lo = c.map_blo;
+    // dim0: the 32 contiguous floats (8 px x 4 ch) of one filter-row window; dim1: output column (windows overlap: stride 2 px = 32 B);
+    // dim2: padded input row; dim3: image
+    const uint64_t dims[4] = {32, (uint64_t)Wo, (uint64_t)Hp, (uint64_t)B};
+    const uint64_t strides[3] = {32, (uint64_t)Wp * 16, (uint64_t)Hp * Wp * 16};
+    const uint32_t box[4] = {32, (uint32_t)kTcTW, (uint32_t)(kTcTH * 2), 1};
+    const uint32_t estr[4] = {1, 1, 2, 1};
+    int rc = make_tensor_map(&maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, estr);
+    if (rc) return rc;
+    TcArgs a;
+    a.bias = c.bias; a.residual = nullptr; a.out = out;
+    a.B = B; a.Ho = Ho; a.Wo = Wo; a.Cout = 64; a.Cin = 32; a.ksize = 7; a.stride = 2; a.pad = 3; a.relu = 1;
+    a.tiles_x = (Wo + kTcTW - 1) / kTcTW;
+    a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
+    a.mode = 1;
+    dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B), 1);
+    conv_tc_kernel<64><<<grid, kTcThreads, tc_smem_bytes(64), st>>>(maps, a);
+    IRN_LAUNCH_CHECK("conv_tc_kernel(stem)");
     return kOk;
 }
 
@@ -274,11 +337,14 @@ static TrunkShapes trunk_shapes(int B, int H, int W) {
     return s;
 }
 
-// Runs stem + maxpool + layer1..4.  feats[0] = after maxpool (x1 of IRNet), feats[1..4] = layer outputs.
-// When `keep` is set every feats[i] lives in its own arena buffer (IRNet taps them); otherwise buffers rotate.
-static int run_trunk(const irn_net* net, const float* x_nhwc, int B, int H, int W, Arena& ar, bool keep, const float* feats[5],
-                     TrunkShapes& sh, cudaStream_t st) {
-    sh = trunk_shapes(B, H, W);
+// Runs input layout transform + stem + maxpool + layer1..4 on x_nchw [B,3,H,W] zero-padded (logically) to Hin x Win.
+// feats[0] = after maxpool (x1 of IRNet), feats[1..4] = layer outputs.  When `keep` is set every feats[i] lives in
+// its own arena buffer (IRNet taps them); otherwise buffers rotate.
+static int run_trunk(const irn_net* net, const float* x_nchw, int B, int H, int W, int Hin, int Win, Arena& ar, bool keep,
+                     const float* feats[5], TrunkShapes& sh, cudaStream_t st) {
+    sh = trunk_shapes(B, Hin, Win);
+    const bool stem_tc = net->conv_mode == 1 && net->stem.stem_tc;
+    float* x_in = stem_tc ? ar.take((size_t)B * (Hin + 6) * (Win + 8) * 4) : ar.take((size_t)B * Hin * Win * 3);
     float* stem_out = ar.take((size_t)B * sh.H1 * sh.W1 * 64);
     float* pool_out = ar.take((size_t)B * sh.H2 * sh.W2 * 64);
     float* t1 = ar.take(sh.max_act);
@@ -287,7 +353,17 @@ static int run_trunk(const irn_net* net, const float* x_nhwc, int B, int H, int 
     float* ping[2] = {ar.take(sh.max_act), ar.take(sh.max_act)};
     if (!ar.ok) return fail(kWorkspace, "network workspace too small");
     int rc;
-    if ((rc = run_conv(net, net->stem, x_nhwc, B, H, W, nullptr, stem_out, true, st, nullptr, nullptr))) return rc;
+    if (stem_tc) {
+        const size_t total = (size_t)B * (Hin + 6) * (Win + 8);
+        nchw_to_nhwc4_halo_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nchw, (float4*)x_in, B, H, W, Hin + 6, Win + 8);
+        IRN_LAUNCH_CHECK("nchw_to_nhwc4_halo_kernel");
+        if ((rc = launch_tc_stem(net->stem, x_in, B, Hin, Win, stem_out, st))) return rc;
+    } else {
+        const size_t total = (size_t)B * Hin * Win * 3;
+        nchw_to_nhwc_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nchw, x_in, B, 3, H, W, Hin, Win);
+        IRN_LAUNCH_CHECK("nchw_to_nhwc_pad_kernel");
+        if ((rc = run_conv(net, net->stem, x_in, B, Hin, Win, nullptr, stem_out, true, st, nullptr, nullptr))) return rc;
+    }
     {
         const size_t total = (size_t)B * sh.H2 * sh.W2 * 16;
         maxpool3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(stem_out, pool_out, B, sh.H1, sh.W1, 64, sh.H2, sh.W2);
@@ -328,7 +404,7 @@ static int run_trunk(const irn_net* net, const float* x_nhwc, int B, int H, int 
 
 static size_t trunk_workspace_floats(int B, int H, int W, bool keep) {
     TrunkShapes s = trunk_shapes(B, H, W);
-    size_t n = (size_t)B * s.H1 * s.W1 * 64 + (size_t)B * s.H2 * s.W2 * 64 + 5 * s.max_act;
+    size_t n = (size_t)B * (H + 6) * (W + 8) * 4 + (size_t)B * s.H1 * s.W1 * 64 + (size_t)B * s.H2 * s.W2 * 64 + 5 * s.max_act;
     if (keep)
         for (int l = 0; l < 4; ++l) n += (size_t)B * s.Hl[l] * s.Wl[l] * kPlanes[l] * 4;
     return n + 64 * 32;   // alignment slack (256 B per buffer)
@@ -433,7 +509,7 @@ extern "C" int irn_irn_net_create(const float* params, size_t n_floats, irn_net*
 
 extern "C" size_t irn_cam_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || (B & 1) || H <= 0 || W <= 0) return 0;
-    return (trunk_workspace_floats(B, H, W, false) + (size_t)B * H * W * 3 + 64) * sizeof(float);
+    return (trunk_workspace_floats(B, H, W, false) + 64) * sizeof(float);
 }
 
 // CAM.forward for P = B/2 (image, flipped image) pairs: x NCHW fp32 [B,3,H,W] -> cam [P,20,ceil(H/16),ceil(W/16)]
@@ -445,16 +521,9 @@ extern "C" int irn_cam_forward(const irn_net* net, const float* x_nchw, int B, i
     if (B <= 0 || (B & 1) || H <= 0 || W <= 0) return fail(kBadArg, "irn_cam_forward: B must be a positive even number (image + flipped image), got B=%d H=%d W=%d", B, H, W);
     if (((uintptr_t)workspace & 255) != 0) return fail(kBadArg, "irn_cam_forward: workspace must be 256-byte aligned");
     Arena ar{(char*)workspace, workspace_bytes};
-    float* x_nhwc = ar.take((size_t)B * H * W * 3);
-    if (!ar.ok) return fail(kWorkspace, "irn_cam_forward: workspace too small");
-    {
-        const size_t total = (size_t)B * H * W * 3;
-        nchw_to_nhwc_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nchw, x_nhwc, B, 3, H, W, H, W);
-        IRN_LAUNCH_CHECK("nchw_to_nhwc_pad_kernel");
-    }
     const float* feats[5];
     TrunkShapes sh;
-    int rc = run_trunk(net, x_nhwc, B, H, W, ar, false, feats, sh, st);
+    int rc = run_trunk(net, x_nchw, B, H, W, H, W, ar, false, feats, sh, st);
     if (rc) return rc;
     const int P = B / 2, h = sh.Hl[3], w = sh.Wl[3];
     const size_t warps = (size_t)P * h * w;
@@ -473,7 +542,7 @@ static size_t irn_head_floats(int B, const TrunkShapes& s) {
     n += g2 * 448;                 // dp1|dp2|dp_up3 concat
     n += g2 * 256;                 // dp7 activations
     n += g2 * 3;                   // edge logits + dp
-    n += (size_t)B * 16 * 2 + 64;  // GN stats
+    n += (size_t)B * 16 * 4 + 64;  // GN sums (fp64)
     return n + 64 * 16;
 }
 
@@ -481,17 +550,22 @@ extern "C" size_t irn_edge_displacement_workspace_bytes(int P, int H, int W, int
     if (P <= 0 || H <= 0 || W <= 0 || H > crop_size || W > crop_size) return 0;
     const int B = 2 * P;
     TrunkShapes s = trunk_shapes(B, crop_size, crop_size);
-    return (trunk_workspace_floats(B, crop_size, crop_size, true) + irn_head_floats(B, s) + (size_t)B * crop_size * crop_size * 3 + 64) * sizeof(float);
+    return (trunk_workspace_floats(B, crop_size, crop_size, true) + irn_head_floats(B, s) + 64) * sizeof(float);
 }
 
 static int run_head(const irn_net* net, const Head& hd, const float* x, int B, int H, int W, float* raw, float* stats, float* dst, int Hd, int Wd, int Cd,
                     int coff, cudaStream_t st) {
     int rc = run_conv(net, hd.conv, x, B, H, W, nullptr, raw, false, st, nullptr, nullptr);
     if (rc) return rc;
-    gn_stats_kernel<<<B * hd.groups, 256, 0, st>>>(raw, stats, H * W, hd.conv.cout, hd.groups, 1e-5f);
-    IRN_LAUNCH_CHECK("gn_stats_kernel");
+    if (hd.conv.cout > 256 || 256 % hd.conv.cout != 0 || hd.groups > 32) return fail(kUnsupported, "GroupNorm head with %d channels / %d groups", hd.conv.cout, hd.groups);
+    IRN_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * hd.groups * 2 * sizeof(double), st));
+    {
+        const int slices = std::max(1, std::min(256, (H * W) / 256));
+        gn_partial_kernel<<<dim3(slices, B), 256, 0, st>>>(raw, (double*)stats, H * W, hd.conv.cout, hd.groups);
+        IRN_LAUNCH_CHECK("gn_partial_kernel");
+    }
     const size_t total = (size_t)B * Hd * Wd * hd.conv.cout;
-    gn_up_relu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(raw, stats, hd.gamma, hd.beta, dst, B, H, W, hd.conv.cout, hd.groups,
+    gn_up_relu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(raw, (const double*)stats, hd.gamma, hd.beta, dst, B, H, W, hd.conv.cout, hd.groups,
                                                                       hd.up, Hd, Wd, Cd, coff);
     IRN_LAUNCH_CHECK("gn_up_relu_kernel");
     return kOk;
@@ -509,16 +583,9 @@ extern "C" int irn_edge_displacement_forward(const irn_net* net, const float* x_
     if (((uintptr_t)workspace & 255) != 0) return fail(kBadArg, "irn_edge_displacement_forward: workspace must be 256-byte aligned");
     const int B = 2 * P, S = crop_size;
     Arena ar{(char*)workspace, workspace_bytes};
-    float* x_nhwc = ar.take((size_t)B * S * S * 3);
-    if (!ar.ok) return fail(kWorkspace, "irn_edge_displacement_forward: workspace too small");
-    {
-        const size_t total = (size_t)B * S * S * 3;
-        nchw_to_nhwc_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nchw, x_nhwc, B, 3, H, W, S, S);
-        IRN_LAUNCH_CHECK("nchw_to_nhwc_pad_kernel");
-    }
     const float* f[5];
     TrunkShapes sh;
-    int rc = run_trunk(net, x_nhwc, B, S, S, ar, true, f, sh, st);
+    int rc = run_trunk(net, x_nchw, B, H, W, S, S, ar, true, f, sh, st);
     if (rc) return rc;
     const int h2 = sh.Hl[0], w2 = sh.Wl[0];   // stride 4 (x1, x2)
     const int h3 = sh.Hl[1], w3 = sh.Wl[1];   // stride 8 (x3)
@@ -531,7 +598,7 @@ extern "C" int irn_edge_displacement_forward(const irn_net* net, const float* x_
     float* dp7a = ar.take(g2 * 256);
     float* elog = ar.take(g2);
     float* dlog = ar.take(g2 * 2);
-    float* stats = ar.take((size_t)B * 16 * 2 + 64);
+    float* stats = ar.take((size_t)B * 16 * 4 + 64);
     if (!ar.ok) return fail(kWorkspace, "irn_edge_displacement_forward: workspace too small");
 
     // edge branch (net/resnet50_irn.py:117-122): every map lands on the stride-4 grid, cropped to edge2's size

@@ -365,7 +365,7 @@ rw_step_tma_kernel(const __grid_constant__ RwMaps maps, const double* __restrict
     }
 }
 
-// ---------------------------------------------------------------- persistent ring step kernel (radius 5, production)
+// ---------------------------------------------------------------- persistent ring step kernel (radius 5, experiment, variant 3)
 // Same arithmetic as rw_step_tma_kernel, restructured so that TMA latency is never exposed: one persistent CTA per SM
 // walks tiles b, b+G, b+2G, ...; warp 4 is a TMA producer that runs ahead through a ring of kRingW weight-class buffers and
 // two state-tile buffers (full/empty mbarriers, no __syncthreads in the loop), warps 0-3 consume.  ~200 KB of loads stay
@@ -559,7 +559,7 @@ static int launch_tma_steps(const RwWorkspace& ws, int n_img, int totc, int h, i
         if (rc) return rc;
     }
     const int tiles_x = (w + kTX - 1) / kTX, tiles_y = (h + kTY - 1) / kTY;
-    if (variant == 2) {   // previous two-buffer kernel, kept for A/B measurements
+    if (variant != 3) {   // production: three 4-warp CTAs per SM, two weight buffers each (measured faster than the ring below for C >= 2)
         const size_t smem = rw_tma_smem_bytes(CH);
         IRN_CUDA(cudaFuncSetAttribute(rw_step_tma_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(tiles_x * tiles_y, n_img);
@@ -714,8 +714,9 @@ extern "C" int irn_random_walk(const float* x, const float* edge, float* out, in
     return walk_impl(x, edge, out, n_img, chan_offsets, h, w, radius, beta, n_iter, workspace, workspace_bytes, 0, (cudaStream_t)stream);
 }
 
-// variant: 0 = production path (persistent TMA-ring step kernel, radius 5), 1 = generic bounds-checked kernel (validation),
-// 2 = the earlier two-buffer TMA kernel (A/B measurements)
+// variant: 0 = production path (TMA-staged register-window step kernel, radius 5), 1 = generic bounds-checked kernel
+// (validation), 3 = persistent one-CTA-per-SM TMA-ring kernel (experiment: 67 vs 50 us/step at C=2 -- four consumer warps
+// per SM cannot hide the LDS -> widen -> DFMA latency; kept for A/B measurements)
 extern "C" int irn_random_walk_variant(const float* x, const float* edge, float* out, int n_img, const int32_t* chan_offsets,
                                        int h, int w, int radius, double beta, int n_iter, void* workspace,
                                        size_t workspace_bytes, int variant, irn_stream_t stream) {

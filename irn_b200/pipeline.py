@@ -46,8 +46,11 @@ class PseudoLabelPipeline:
         N = xs[0].shape[0] // 2
         # ---- C2/C3: CAM forward per scale, in sub-batches of image pairs
         cams = []
-        for x in xs:
-            outs = [self.cam.forward_batch(x[2 * i:2 * min(i + self.cam_sub, N)]) for i in range(0, N, self.cam_sub)]
+        for x, s in zip(xs, self.scales):
+            # sub-batch so that every forward sees about the same number of pixels (cam_sub images at scale 2.0):
+            # small scales batch more images to keep all SMs busy, large scales bound the activation arena
+            sub = max(1, int(self.cam_sub * (2.0 / s) ** 2))
+            outs = [self.cam.forward_batch(x[2 * i:2 * min(i + sub, N)]) for i in range(0, N, sub)]
             cams.append(torch.cat(outs, 0))
         # ---- C4: merge + normalise per image (classes present differ per image)
         keys, strided, highres = [], [], []
@@ -59,8 +62,9 @@ class PseudoLabelPipeline:
         # ---- I1/I2: edge + displacement
         x1 = xs[self.scales.index(1.0)]
         edges = []
-        for i in range(0, N, self.cam_sub):
-            e, _ = self.irn.forward_batch(x1[2 * i:2 * min(i + self.cam_sub, N)])
+        irn_sub = self.cam_sub * 4
+        for i in range(0, N, irn_sub):
+            e, _ = self.irn.forward_batch(x1[2 * i:2 * min(i + irn_sub, N)])
             edges.append(e[:, 0])
         edges = torch.cat(edges, 0)
         # ---- R1-R6: batched walk (sub-batches sized so the weights stay L2-resident)

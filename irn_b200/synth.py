@@ -72,7 +72,8 @@ def image(index, H=512, W=512):
         cy, cx = rng.uniform(0.15, 0.85) * H, rng.uniform(0.15, 0.85) * W
         ry, rx = rng.uniform(0.06, 0.3) * H, rng.uniform(0.06, 0.3) * W
         col = rng.uniform(0, 255, 3).astype(np.float32)
-        m = 1.0 / (1.0 + np.exp(8.0 * (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 - 1.0)))
+        with np.errstate(over="ignore"):   # exp overflow -> inf -> m = 0 exactly, intended
+            m = 1.0 / (1.0 + np.exp(8.0 * (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 - 1.0)))
         img = img * (1 - m[..., None]) + col * m[..., None]
     img += rng.normal(0, 8, img.shape).astype(np.float32)
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
@@ -106,7 +107,8 @@ def edge_map(h, w, kind="bimodal", seed=0):
     else:
         z = _blur(rng.standard_normal((h, w)).astype(np.float32), 9)
         z = z / (z.std() + 1e-6)
-        e = 1 / (1 + np.exp(30 * (np.abs(z) - 0.12)))   # thin ridges where |z| is small
+        with np.errstate(over="ignore"):
+            e = 1 / (1 + np.exp(30 * (np.abs(z) - 0.12)))   # thin ridges where |z| is small
     return e.astype(np.float32)[None]
 
 

@@ -33,7 +33,7 @@ def test_edge_to_affinity_exact(cuda_dev):
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(golden_path("rw_*.npz"))), ids=os.path.basename)
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 3])
 def test_random_walk_vs_reference(cuda_dev, path, variant):
     g = np.load(path)
     x, edge = g["x"], g["edge"]
@@ -65,7 +65,7 @@ def test_walk_shapes_and_properties(cuda_dev, h, w):
     x = synth.seeds(C, h, w, h)
     a = indexing.random_walk_batch(_t(x, cuda_dev), _t(e, cuda_dev), [0, C], n_iter=16, variant=0).cpu().numpy()
     b = indexing.random_walk_batch(_t(x, cuda_dev), _t(e, cuda_dev), [0, C], n_iter=16, variant=1).cpu().numpy()
-    c = indexing.random_walk_batch(_t(x, cuda_dev), _t(e, cuda_dev), [0, C], n_iter=16, variant=2).cpu().numpy()
+    c = indexing.random_walk_batch(_t(x, cuda_dev), _t(e, cuda_dev), [0, C], n_iter=16, variant=3).cpu().numpy()
     assert np.abs(a - b).max() < 1e-6 and np.array_equal(a, c)   # ring and two-buffer kernels do identical arithmetic
     truth = oi.propagate_stencil(x, e, 5, 10, 16).reshape(C, h, w)
     assert np.abs(a - truth).max() < 1e-6
