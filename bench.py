@@ -89,7 +89,8 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_threads():
-    return min(os.cpu_count(), int(os.environ.get("IRN_CPU_THREADS", "32"))   # measured on the B200 host: 128 torch threads are 50x slower than 16-32)
+    # measured on the B200 host (profiles/r01_cpu_threads_probe.txt): 128 torch threads are 50x slower than 16-32
+    return min(os.cpu_count(), int(os.environ.get("IRN_CPU_THREADS", "32")))
 
 
 def dense_walk_sample(cam, edge):
