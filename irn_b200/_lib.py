@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libirn_b200.so")
+LIB_PATH = os.environ.get("IRN_B200_LIB", os.path.join(_HERE, "libirn_b200.so"))   # override: A/B builds during development
 
 _lib = None
 

@@ -273,9 +273,16 @@ gn_partial_kernel(const float* __restrict__ x, double* __restrict__ sums, int HW
         s += v;
         ss += v * v;
     }
-    const int g = c / (C / G);
-    atomicAdd(&sh[g][0], s);
-    atomicAdd(&sh[g][1], ss);
+    const int cpg = C / G;            // 8 or 16 consecutive lanes share a group (C >= 32, so a warp never wraps channels)
+    for (int o = 1; o < cpg; o <<= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    const int g = c / cpg;
+    if ((c % cpg) == 0) {
+        atomicAdd(&sh[g][0], s);
+        atomicAdd(&sh[g][1], ss);
+    }
     __syncthreads();
     if (threadIdx.x < G) {
         atomicAdd(&sums[(size_t)(b * G + threadIdx.x) * 2], sh[threadIdx.x][0]);

@@ -204,6 +204,55 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[s]);
         }
+#ifdef IRN_TC_EPILOGUE_DIRECT
+        // ---- epilogue
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;          // tile row = output pixel
+        const int oy = oy0 + row / kTcTW, ox = ox0 + row % kTcTW;
+        const bool valid = oy < args.Ho && ox < args.Wo;
+        const size_t pix = ((size_t)b * args.Ho + oy) * args.Wo + ox;
+        float* outp = args.out + pix * args.Cout + n0;
+        const float* resp = args.residual ? args.residual + pix * args.Cout + n0 : nullptr;
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; ++cc) {
+            uint32_t v[32], u[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
+            tc_ld32(taddr, v);
+            tc_ld32(taddr + 2u * BN, u);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (KB >= 2) {   // the odd-k-block accumulator exists only when there is more than one k-block
+                uint32_t t2[32];
+                tc_ld32(taddr + (uint32_t)BN, t2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t2[j]));
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]); o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
+                    if (args.bias) {
+                        const float4 bi = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + cc * 32 + j));
+                        o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w;
+                    }
+                    if (resp) {
+                        const float4 rr = __ldg(reinterpret_cast<const float4*>(resp + cc * 32 + j));
+                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                    }
+                    if (args.relu) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    }
+                    *reinterpret_cast<float4*>(outp + cc * 32 + j) = o;
+                }
+            }
+        }
+    }
+#else
         // ---- epilogue.  Phase 1: TMEM -> registers (thread = one tile row), sum the three accumulators, park the
         // 32 x BN block of this warp in shared memory (the pipeline stages are idle once acc_full fired).  Phase 2: the warp
         // walks its 32 rows with lanes across the channels, so bias / residual loads and the output stores are full
@@ -263,6 +312,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             }
         }
     }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
