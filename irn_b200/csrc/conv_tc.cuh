@@ -21,7 +21,6 @@ namespace irn {
 
 constexpr int kTcTW = 16, kTcTH = 8;          // spatial tile: 128 output pixels
 constexpr int kTcBK = 32;                     // fp32 channels per k-block = 128 bytes = one swizzle atom
-constexpr int kTcStages = 3;
 constexpr int kTcThreads = 192;
 
 struct TcMaps {
@@ -39,8 +38,8 @@ struct TcArgs {
     int mode;   // 0: NHWC input, one k-block per (tap, 32-channel slice); 1: stem, NHWC4 zero-haloed input, one k-block per filter row
 };
 
-constexpr size_t tc_smem_bytes(int BN) {
-    return 1024 /*align*/ + (size_t)kTcStages * (2 * 16384 + 2 * (size_t)BN * 128) + 256;
+constexpr size_t tc_smem_bytes(int BN, int stages) {
+    return 1024 /*align*/ + (size_t)stages * (2 * 16384 + 2 * (size_t)BN * 128) + 256;
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -94,13 +93,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// STAGES: smem pipeline depth.  NACC: 3 = two alternating hi*hi accumulators + one for the cross terms; 2 = one hi*hi + cross
+// (short K: few accumulation steps, and 2 x BN TMEM columns let several CTAs share an SM so their fixed latencies overlap).
+template <int BN, int STAGES, int NACC>
+__global__ void __launch_bounds__(kTcThreads, (STAGES == 2 && BN == 64) ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     unsigned char* smem = tc_smem_raw;   // dynamic smem base is 1024-aligned by the attribute; checked below
     constexpr int kStageBytes = 2 * 16384 + 2 * BN * 128;
-    constexpr int kTmemCols = BN == 128 ? 512 : 256;   // three BN-column fp32 accumulators, power-of-two allocation
+    constexpr int kTcStages = STAGES;
+    constexpr int kTmemCols = NACC * BN <= 128 ? 128 : (NACC * BN <= 256 ? 256 : 512);   // power-of-two allocation
+    constexpr uint32_t kCrossCol = (NACC - 1) * BN;
     uint64_t* bars = (uint64_t*)(smem + kTcStages * kStageBytes);
     uint64_t* full = bars;                    // [S] TMA landed
     uint64_t* split = bars + kTcStages;       // [S] A_hi / A_lo written
@@ -175,9 +178,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                     // steps into one accumulator (measured ~7e-6 rel. at K=1152 with a single accumulator).  So the
                     // large hi*hi terms alternate between two accumulators (even / odd k-blocks) and the small
                     // cross terms get a third; the epilogue adds the three in IEEE fp32.
-                    tc_mma_tf32(tmem_base + (uint32_t)((kb & 1) * BN), da_hi, db_hi, idesc, (kb >= 2 || k4 != 0) ? 1u : 0u);
-                    tc_mma_tf32(tmem_base + 2u * BN, da_lo, db_hi, idesc, (kb | k4) != 0);
-                    tc_mma_tf32(tmem_base + 2u * BN, da_hi, db_lo, idesc, 1);
+                    tc_mma_tf32(tmem_base + (NACC == 3 ? (uint32_t)((kb & 1) * BN) : 0u), da_hi, db_hi, idesc, (kb >= (NACC == 3 ? 2 : 1) || k4 != 0) ? 1u : 0u);
+                    tc_mma_tf32(tmem_base + kCrossCol, da_lo, db_hi, idesc, (kb | k4) != 0);
+                    tc_mma_tf32(tmem_base + kCrossCol, da_hi, db_lo, idesc, 1);
                 }
                 tc_commit(&empty[s]);      // arrives when the MMAs above have finished reading the stage
             }
@@ -204,7 +207,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[s]);
         }
-#ifdef IRN_TC_EPILOGUE_DIRECT
         // ---- epilogue
         mbar_wait(acc_full, 0);
         tc_fence_after();
@@ -220,9 +222,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             uint32_t v[32], u[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
             tc_ld32(taddr, v);
-            tc_ld32(taddr + 2u * BN, u);
+            tc_ld32(taddr + kCrossCol, u);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (KB >= 2) {   // the odd-k-block accumulator exists only when there is more than one k-block
+            if (NACC == 3 && KB >= 2) {   // the odd-k-block accumulator exists only when there is more than one k-block
                 uint32_t t2[32];
                 tc_ld32(taddr + (uint32_t)BN, t2);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -252,67 +254,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             }
         }
     }
-#else
-        // ---- epilogue.  Phase 1: TMEM -> registers (thread = one tile row), sum the three accumulators, park the
-        // 32 x BN block of this warp in shared memory (the pipeline stages are idle once acc_full fired).  Phase 2: the warp
-        // walks its 32 rows with lanes across the channels, so bias / residual loads and the output stores are full
-        // 512-byte (256 for BN=64) coalesced segments instead of 32 scattered 16-byte pieces per instruction.
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        constexpr int kLd = BN + 4;             // padded row stride (floats): conflict-free float4 rows
-        float* stg = reinterpret_cast<float*>(smem) + (size_t)q * 32 * kLd;
-#pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc) {
-            uint32_t v[32], u[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
-            tc_ld32(taddr, v);
-            tc_ld32(taddr + 2u * BN, u);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (KB >= 2) {   // the odd-k-block accumulator exists only when there is more than one k-block
-                uint32_t t2[32];
-                tc_ld32(taddr + (uint32_t)BN, t2);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t2[j]));
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 o;
-                o.x = __uint_as_float(v[j]) + __uint_as_float(u[j]);
-                o.y = __uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1]);
-                o.z = __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]);
-                o.w = __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3]);
-                *reinterpret_cast<float4*>(stg + lane * kLd + cc * 32 + j) = o;
-            }
-        }
-        __syncwarp();
-        constexpr int kLanesPerRow = BN / 4;            // 32 (BN=128) or 16 (BN=64)
-        constexpr int kRowsPerIter = 32 / kLanesPerRow;
-        const int sub = lane / kLanesPerRow, col = (lane % kLanesPerRow) * 4;
-        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (args.bias) bi = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + col));
-#pragma unroll 4
-        for (int r0 = 0; r0 < 32; r0 += kRowsPerIter) {
-            const int r = r0 + sub;
-            const int row = q * 32 + r;
-            const int oy = oy0 + row / kTcTW, ox = ox0 + row % kTcTW;
-            if (oy < args.Ho && ox < args.Wo) {
-                const size_t off = (((size_t)b * args.Ho + oy) * args.Wo + ox) * args.Cout + n0 + col;
-                float4 o = *reinterpret_cast<const float4*>(stg + r * kLd + col);
-                o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w;
-                if (args.residual) {
-                    const float4 rr = __ldg(reinterpret_cast<const float4*>(args.residual + off));
-                    o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                }
-                if (args.relu) {
-                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                }
-                *reinterpret_cast<float4*>(args.out + off) = o;
-            }
-        }
-    }
-#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {

@@ -25,7 +25,8 @@ struct Conv {
     float* w_hi = nullptr;
     float* w_lo = nullptr;
     int bn = 0;              // N tile (64 or 128); 0 = not eligible
-    CUtensorMap map_bhi, map_blo;
+    CUtensorMap map_bhi, map_blo;        // box {32, bn}
+    CUtensorMap map_bhi64, map_blo64;    // box {32, 64} (short-K configuration)
     bool stem_tc = false;    // 7x7/s2 stem repacked as 7 k-blocks of (8 taps x 4 channels) over a zero-haloed NHWC4 input
 };
 
@@ -144,6 +145,9 @@ static int read_conv(irn_net* net, Reader& rd, Conv& c, int cin, int cout, int k
         const uint32_t box[2] = {(uint32_t)kTcBK, (uint32_t)c.bn};
         if ((rc = make_tensor_map(&c.map_bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
         if ((rc = make_tensor_map(&c.map_blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        const uint32_t box64[2] = {(uint32_t)kTcBK, 64};
+        if ((rc = make_tensor_map(&c.map_bhi64, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_hi, dims, strides, box64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tensor_map(&c.map_blo64, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_lo, dims, strides, box64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     }
     return kOk;
 }
@@ -215,17 +219,17 @@ static int read_head(irn_net* net, Reader& rd, Head& h, int cin, int cout, int g
 // ------------------------------------------------------------------ launch helpers
 static inline int conv_out(int n, int k, int s, int p) { return (n + 2 * p - k) / s + 1; }
 
-template <int BN>
+template <int BN, int STAGES, int NACC>
 static int launch_tc(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
                      cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        IRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(BN)));
+        IRN_CUDA(cudaFuncSetAttribute((conv_tc_kernel<BN, STAGES, NACC>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(BN, STAGES)));
         attr_set = true;
     }
     TcMaps maps;
-    maps.b_hi = c.map_bhi;
-    maps.b_lo = c.map_blo;
+    maps.b_hi = BN == 64 && c.bn == 128 ? c.map_bhi64 : c.map_bhi;
+    maps.b_lo = BN == 64 && c.bn == 128 ? c.map_blo64 : c.map_blo;
     const uint64_t dims[4] = {(uint64_t)c.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)c.cin * 4, (uint64_t)W * c.cin * 4, (uint64_t)H * W * c.cin * 4};
     const uint32_t box[4] = {(uint32_t)kTcBK, (uint32_t)(kTcTW * c.stride), (uint32_t)(kTcTH * c.stride), 1};
@@ -240,7 +244,7 @@ static int launch_tc(const Conv& c, const float* in, int B, int H, int W, int Ho
     a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
     a.mode = 0;
     dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B), (unsigned)(c.cout / BN));
-    conv_tc_kernel<BN><<<grid, kTcThreads, tc_smem_bytes(BN), st>>>(maps, a);
+    conv_tc_kernel<BN, STAGES, NACC><<<grid, kTcThreads, tc_smem_bytes(BN, STAGES), st>>>(maps, a);
     IRN_LAUNCH_CHECK("conv_tc_kernel");
     return kOk;
 }
@@ -249,7 +253,7 @@ static int launch_tc(const Conv& c, const float* in, int B, int H, int W, int Ho
 static int launch_tc_stem(const Conv& c, const float* x4, int B, int Hin, int Win, float* out, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        IRN_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(64)));
+        IRN_CUDA(cudaFuncSetAttribute((conv_tc_kernel<64, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(64, 3)));
         attr_set = true;
     }
     const int Hp = Hin + 6, Wp = Win + 8;
@@ -272,7 +276,7 @@ static int launch_tc_stem(const Conv& c, const float* x4, int B, int Hin, int Wi
     a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
     a.mode = 1;
     dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B), 1);
-    conv_tc_kernel<64><<<grid, kTcThreads, tc_smem_bytes(64), st>>>(maps, a);
+    conv_tc_kernel<64, 3, 3><<<grid, kTcThreads, tc_smem_bytes(64, 3), st>>>(maps, a);
     IRN_LAUNCH_CHECK("conv_tc_kernel(stem)");
     return kOk;
 }
@@ -286,8 +290,15 @@ static int run_conv(const irn_net* net, const Conv& c, const float* in, int B, i
     g.Cout = c.cout; g.k = c.k; g.stride = c.stride; g.pad = c.pad;
     if (Ho_) *Ho_ = g.Ho;
     if (Wo_) *Wo_ = g.Wo;
-    if (net->conv_mode == 1 && c.bn == 128) return launch_tc<128>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
-    if (net->conv_mode == 1 && c.bn == 64) return launch_tc<64>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
+    if (net->conv_mode == 1 && c.bn) {
+        // short reductions (K <= 256) are latency-bound per tile: 64-wide tiles with a 2-stage pipeline and two TMEM
+        // accumulators let two CTAs share an SM; long reductions use the 3-stage, 3-accumulator configuration
+        const int K = c.k * c.k * c.cin;
+        if (K <= 128) return launch_tc<64, 2, 2>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
+        if (K <= 256) return launch_tc<64, 2, 3>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
+        if (c.bn == 128) return launch_tc<128, 3, 3>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
+        return launch_tc<64, 3, 3>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
+    }
     const int M = B * g.Ho * g.Wo;
     dim3 grid((M + kBM - 1) / kBM, (c.cout + kBN - 1) / kBN);
     if (c.cin % 16 == 0)
