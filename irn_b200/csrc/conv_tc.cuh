@@ -207,16 +207,40 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[s]);
         }
-        // ---- epilogue
+        // ---- epilogue.  The direct form (thread = tile row, 128-byte pieces of 32 different rows per instruction) is bound
+        // by L1 wavefronts: 32 per load/store instruction instead of 4.  So: phase 1 parks the warp's 32 x BN block in shared
+        // memory (the pipeline stages are idle once acc_full fired); phase 2 walks the rows with lanes across the channels --
+        // bias / residual loads and output stores are full coalesced row segments.  The residual rows are prefetched into
+        // registers 16 row-steps at a time, the first batch before the accumulator is even ready.
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        constexpr int kLd = BN + 4;             // padded row stride (floats): conflict-free float4 rows
+        constexpr int kLanesPerRow = BN / 4;    // 32 (BN=128) or 16 (BN=64)
+        constexpr int kRowsPerIter = 32 / kLanesPerRow;
+        constexpr int kIters = 32 / kRowsPerIter;
+        constexpr int kRB = 16;
+        const int sub = lane / kLanesPerRow, col = (lane % kLanesPerRow) * 4;
+        float* stg = reinterpret_cast<float*>(smem) + (size_t)q * 32 * kLd;
+        float4 res[kRB];
+        auto row_offset = [&](int it, bool& ok) -> size_t {
+            const int row = q * 32 + it * kRowsPerIter + sub;
+            const int oy = oy0 + row / kTcTW, ox = ox0 + row % kTcTW;
+            ok = oy < args.Ho && ox < args.Wo;
+            return (((size_t)b * args.Ho + oy) * args.Wo + ox) * args.Cout + n0 + col;
+        };
+        auto prefetch = [&](int base) {
+#pragma unroll
+            for (int i = 0; i < kRB; ++i) {
+                bool ok;
+                const size_t off = row_offset(base + i, ok);
+                res[i] = (ok && args.residual) ? __ldg(reinterpret_cast<const float4*>(args.residual + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        prefetch(0);
+        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (args.bias) bi = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + col));
+
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;          // tile row = output pixel
-        const int oy = oy0 + row / kTcTW, ox = ox0 + row % kTcTW;
-        const bool valid = oy < args.Ho && ox < args.Wo;
-        const size_t pix = ((size_t)b * args.Ho + oy) * args.Wo + ox;
-        float* outp = args.out + pix * args.Cout + n0;
-        const float* resp = args.residual ? args.residual + pix * args.Cout + n0 : nullptr;
 #pragma unroll 1
         for (int cc = 0; cc < BN / 32; ++cc) {
             uint32_t v[32], u[32];
@@ -232,24 +256,30 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t2[j]));
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-            if (valid) {
+            for (int j = 0; j < 32; j += 4) {
+                float4 o;
+                o.x = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                o.y = __uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1]);
+                o.z = __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]);
+                o.w = __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3]);
+                *reinterpret_cast<float4*>(stg + lane * kLd + cc * 32 + j) = o;
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int base = 0; base < kIters; base += kRB) {
+            if (base > 0) prefetch(base);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    o.x = __uint_as_float(v[j]); o.y = __uint_as_float(v[j + 1]); o.z = __uint_as_float(v[j + 2]); o.w = __uint_as_float(v[j + 3]);
-                    if (args.bias) {
-                        const float4 bi = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + cc * 32 + j));
-                        o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w;
-                    }
-                    if (resp) {
-                        const float4 rr = __ldg(reinterpret_cast<const float4*>(resp + cc * 32 + j));
-                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                    }
+            for (int i = 0; i < kRB; ++i) {
+                bool ok;
+                const size_t off = row_offset(base + i, ok);
+                if (ok) {
+                    float4 o = *reinterpret_cast<const float4*>(stg + ((base + i) * kRowsPerIter + sub) * kLd + col);
+                    o.x += bi.x + res[i].x; o.y += bi.y + res[i].y; o.z += bi.z + res[i].z; o.w += bi.w + res[i].w;
                     if (args.relu) {
                         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                     }
-                    *reinterpret_cast<float4*>(outp + cc * 32 + j) = o;
+                    *reinterpret_cast<float4*>(args.out + off) = o;
                 }
             }
         }
