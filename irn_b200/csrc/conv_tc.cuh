@@ -96,7 +96,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // STAGES: smem pipeline depth.  NACC: 3 = two alternating hi*hi accumulators + one for the cross terms; 2 = one hi*hi + cross
 // (short K: few accumulation steps, and 2 x BN TMEM columns let several CTAs share an SM so their fixed latencies overlap).
 template <int BN, int STAGES, int NACC>
-__global__ void __launch_bounds__(kTcThreads, (STAGES == 2 && BN == 64) ? 2 : 1)
+__global__ void __launch_bounds__(kTcThreads, BN == 64 ? (STAGES == 1 ? 3 : (STAGES == 2 ? 2 : 1)) : 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     unsigned char* smem = tc_smem_raw;   // dynamic smem base is 1024-aligned by the attribute; checked below
@@ -112,12 +112,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     uint32_t* tmem_slot = (uint32_t*)(bars + 3 * kTcStages + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
+    // 1-D grid, N-tile fastest: the CTAs that share an activation tile (and write neighbouring channel segments of the same
+    // pixels) run at the same time, so the tile is fetched from HBM once and served to the others from L2
+    const int n_tiles = args.Cout / BN;
+    const int tile = blockIdx.x / n_tiles;
     const int tx = tile % args.tiles_x;
     const int ty = (tile / args.tiles_x) % args.tiles_y;
     const int b = tile / (args.tiles_x * args.tiles_y);
     const int ox0 = tx * kTcTW, oy0 = ty * kTcTH;
-    const int n0 = blockIdx.y * BN;
+    const int n0 = (blockIdx.x % n_tiles) * BN;
     const int cblocks = args.Cin / kTcBK;
     const int KB = args.mode == 1 ? args.ksize : args.ksize * args.ksize * cblocks;
 

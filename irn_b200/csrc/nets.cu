@@ -243,7 +243,7 @@ static int launch_tc(const Conv& c, const float* in, int B, int H, int W, int Ho
     a.tiles_x = (Wo + kTcTW - 1) / kTcTW;
     a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
     a.mode = 0;
-    dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B), (unsigned)(c.cout / BN));
+    dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B * (c.cout / BN)));
     conv_tc_kernel<BN, STAGES, NACC><<<grid, kTcThreads, tc_smem_bytes(BN, STAGES), st>>>(maps, a);
     IRN_LAUNCH_CHECK("conv_tc_kernel");
     return kOk;

@@ -223,7 +223,10 @@ __device__ __forceinline__ void static_for(F&& f) {
 
 constexpr int kR = 4;                 // stencil reach for radius 5
 constexpr int kTX = 32;               // tile width = one warp
-constexpr int kPY = 4;                // rows per thread (register window)
+#ifndef IRN_RW_PY
+#define IRN_RW_PY 4
+#endif
+constexpr int kPY = IRN_RW_PY;        // rows per thread (register window)
 constexpr int kWarps = 4;
 constexpr int kTY = kPY * kWarps;     // 16
 constexpr int kSW = kTX + 2 * kR;     // 40 columns staged (x0-4 .. x0+35)
