@@ -295,4 +295,238 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent variant for short reductions (K <= ~640: the 1x1 bottleneck convs and layer1's 3x3).  With 2-20 k-blocks per
+// tile the one-tile-per-CTA kernel above is dominated by per-CTA fixed latencies (measured: 9.6 us per 128x64 tile of the
+// 64->256 conv, tensor pipe 9 % busy, DRAM 27 %, warps parked on barriers).  Here one CTA per SM walks tiles
+// c, c+G, c+2G, ... (N-tile fastest) with every stage decoupled:
+//   warp 0      TMA producer, runs ahead through the smem ring across tile boundaries
+//   warps 2-5   hi/lo split of the activation k-blocks
+//   warp 1      MMA issuer; two TMEM accumulator sets (hi*hi | cross terms each) ping-pong between consecutive tiles
+//   warps 6-9   epilogue: TMEM -> shared staging -> coalesced (+bias +residual, ReLU) stores, overlapped with the next
+//               tile's loads and MMAs; the residual rows are prefetched before the accumulator is ready
+constexpr int kTcPersistThreads = 320;
+
+template <int BN>
+struct TcPersistCfg {
+    static constexpr int kStages = BN == 128 ? 2 : 3;
+    static constexpr int kStageBytes = 2 * 16384 + 2 * BN * 128;
+    static constexpr int kLd = BN + 4;
+    static constexpr int kStagingBytes = 128 * kLd * 4;
+    static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + kStagingBytes + 256;
+    static constexpr int kTmemCols = 4 * BN <= 256 ? 256 : 512;   // 2 sets x (main + cross) x BN columns
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kTcPersistThreads, 1)
+conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
+    using Cfg = TcPersistCfg<BN>;
+    constexpr int S = Cfg::kStages;
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    unsigned char* smem = tc_smem_raw;
+    float* staging = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes);
+    uint64_t* bars = (uint64_t*)(smem + S * Cfg::kStageBytes + Cfg::kStagingBytes);
+    uint64_t* full = bars;                 // [S]
+    uint64_t* split = bars + S;            // [S]
+    uint64_t* empty = bars + 2 * S;        // [S]
+    uint64_t* tmem_full = bars + 3 * S;    // [2] MMA -> epilogue
+    uint64_t* tmem_empty = bars + 3 * S + 2;   // [2] epilogue -> MMA
+    uint32_t* tmem_slot = (uint32_t*)(bars + 3 * S + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = args.Cout / BN;
+    const int m_tiles = args.tiles_x * args.tiles_y * args.B;
+    const int total = m_tiles * n_tiles;
+    const int cblocks = args.Cin / kTcBK;
+    const int KB = args.ksize * args.ksize * cblocks;
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) __trap();
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split[s], 4);
+            mbar_init(&empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto tile_coords = [&](int id, int& b, int& oy0, int& ox0, int& n0) {
+        const int m = id / n_tiles;
+        n0 = (id % n_tiles) * BN;
+        ox0 = (m % args.tiles_x) * kTcTW;
+        oy0 = ((m / args.tiles_x) % args.tiles_y) * kTcTH;
+        b = m / (args.tiles_x * args.tiles_y);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&maps.a);
+            tma_prefetch_desc(&maps.b_hi);
+            tma_prefetch_desc(&maps.b_lo);
+            uint32_t g = 0;   // k-blocks issued so far (ring position)
+            for (int id = blockIdx.x; id < total; id += gridDim.x) {
+                int b, oy0, ox0, n0;
+                tile_coords(id, b, oy0, ox0, n0);
+                for (int kb = 0; kb < KB; ++kb, ++g) {
+                    const uint32_t s = g % S, it = g / S;
+                    mbar_wait(&empty[s], (it & 1) ^ 1);
+                    unsigned char* st = smem + s * Cfg::kStageBytes;
+                    const int tap = kb / cblocks, cb = kb % cblocks;
+                    const int r = tap / args.ksize, ss = tap % args.ksize;
+                    mbar_arrive_expect_tx(&full[s], 16384u + 2u * BN * 128u);
+                    tma_load_4d(st, &maps.a, &full[s], cb * kTcBK, ox0 * args.stride - args.pad + ss, oy0 * args.stride - args.pad + r, b);
+                    tma_load_2d(st + 32768, &maps.b_hi, &full[s], kb * kTcBK, n0);
+                    tma_load_2d(st + 32768 + BN * 128, &maps.b_lo, &full[s], kb * kTcBK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc(128, BN);
+            uint32_t g = 0, ti = 0;
+            for (int id = blockIdx.x; id < total; id += gridDim.x, ++ti) {
+                const uint32_t set = ti & 1, use = ti >> 1;
+                mbar_wait(&tmem_empty[set], (use & 1) ^ 1);     // the epilogue drained this accumulator set
+                tc_fence_after();
+                const uint32_t acc = tmem_base + set * (2u * BN);
+                for (int kb = 0; kb < KB; ++kb, ++g) {
+                    const uint32_t s = g % S, it = g / S;
+                    mbar_wait(&full[s], it & 1);
+                    mbar_wait(&split[s], it & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes), a_lo = a_hi + 16384;
+                    const uint32_t b_hi = a_hi + 32768, b_lo = b_hi + BN * 128;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const uint64_t da_hi = tc_smem_desc(a_hi + k4 * 32), da_lo = tc_smem_desc(a_lo + k4 * 32);
+                        const uint64_t db_hi = tc_smem_desc(b_hi + k4 * 32), db_lo = tc_smem_desc(b_lo + k4 * 32);
+                        tc_mma_tf32(acc, da_hi, db_hi, idesc, (kb | k4) != 0);
+                        tc_mma_tf32(acc + BN, da_lo, db_hi, idesc, (kb | k4) != 0);
+                        tc_mma_tf32(acc + BN, da_hi, db_lo, idesc, 1);
+                    }
+                    tc_commit(&empty[s]);
+                }
+                tc_commit(&tmem_full[set]);
+            }
+        }
+    } else if (warp < 6) {
+        // ---- split warps
+        const int t = threadIdx.x - 64;   // 0..127
+        uint32_t g = 0;
+        for (int id = blockIdx.x; id < total; id += gridDim.x) {
+            for (int kb = 0; kb < KB; ++kb, ++g) {
+                const uint32_t s = g % S, it = g / S;
+                mbar_wait(&full[s], it & 1);
+                float4* a = reinterpret_cast<float4*>(smem + s * Cfg::kStageBytes);
+                float4* lo = reinterpret_cast<float4*>(smem + s * Cfg::kStageBytes + 16384);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 v = a[i * 128 + t];
+                    float4 h, l;
+                    h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+                    l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+                    a[i * 128 + t] = h;
+                    lo[i * 128 + t] = l;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split[s]);
+            }
+        }
+    } else {
+        // ---- epilogue warps 6..9 (TMEM lane quarter = warp % 4)
+        const int q = warp & 3;
+        constexpr int kLd = Cfg::kLd;
+        constexpr int kLanesPerRow = BN / 4;
+        constexpr int kRowsPerIter = 32 / kLanesPerRow;
+        constexpr int kIters = 32 / kRowsPerIter;
+        constexpr int kRB = 16;
+        const int sub = lane / kLanesPerRow, col = (lane % kLanesPerRow) * 4;
+        float* stg = staging + (size_t)q * 32 * kLd;
+        uint32_t ti = 0;
+        for (int id = blockIdx.x; id < total; id += gridDim.x, ++ti) {
+            int b, oy0, ox0, n0;
+            tile_coords(id, b, oy0, ox0, n0);
+            const uint32_t set = ti & 1, use = ti >> 1;
+            float4 res[kRB];
+            auto row_offset = [&](int it, bool& ok) -> size_t {
+                const int row = q * 32 + it * kRowsPerIter + sub;
+                const int oy = oy0 + row / kTcTW, ox = ox0 + row % kTcTW;
+                ok = oy < args.Ho && ox < args.Wo;
+                return (((size_t)b * args.Ho + oy) * args.Wo + ox) * args.Cout + n0 + col;
+            };
+            auto prefetch = [&](int base) {
+#pragma unroll
+                for (int i = 0; i < kRB; ++i) {
+                    bool ok;
+                    const size_t off = row_offset(base + i, ok);
+                    res[i] = (ok && args.residual) ? __ldg(reinterpret_cast<const float4*>(args.residual + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            prefetch(0);
+            float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (args.bias) bi = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + col));
+
+            mbar_wait(&tmem_full[set], use & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < BN / 32; ++cc) {
+                uint32_t v[32], u[32];
+                const uint32_t taddr = tmem_base + set * (2u * BN) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
+                tc_ld32(taddr, v);
+                tc_ld32(taddr + BN, u);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    o.x = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                    o.y = __uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1]);
+                    o.z = __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]);
+                    o.w = __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3]);
+                    *reinterpret_cast<float4*>(stg + lane * kLd + cc * 32 + j) = o;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[set]);   // accumulator set free for the tile after next
+#pragma unroll 1
+            for (int base = 0; base < kIters; base += kRB) {
+                if (base > 0) prefetch(base);
+#pragma unroll
+                for (int i = 0; i < kRB; ++i) {
+                    bool ok;
+                    const size_t off = row_offset(base + i, ok);
+                    if (ok) {
+                        float4 o = *reinterpret_cast<const float4*>(stg + ((base + i) * kRowsPerIter + sub) * kLd + col);
+                        o.x += bi.x + res[i].x; o.y += bi.y + res[i].y; o.z += bi.z + res[i].z; o.w += bi.w + res[i].w;
+                        if (args.relu) {
+                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                        }
+                        *reinterpret_cast<float4*>(args.out + off) = o;
+                    }
+                }
+            }
+            __syncwarp();   // staging rows are rewritten by the next tile's phase 1
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
+    }
+}
+
 }  // namespace irn

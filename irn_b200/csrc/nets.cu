@@ -8,6 +8,7 @@
 // workspace.  The host walks the fixed topology and enqueues kernels on the caller's stream; nothing
 // synchronises.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -281,6 +282,41 @@ static int launch_tc_stem(const Conv& c, const float* x4, int B, int Hin, int Wi
     return kOk;
 }
 
+template <int BN>
+static int launch_tc_persist(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out,
+                             bool relu, cudaStream_t st) {
+    static bool attr_set = false;
+    static int n_sm = 0;
+    if (!attr_set) {
+        IRN_CUDA(cudaFuncSetAttribute(conv_tc_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcPersistCfg<BN>::kSmem));
+        int dev = 0;
+        IRN_CUDA(cudaGetDevice(&dev));
+        IRN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        attr_set = true;
+    }
+    TcMaps maps;
+    maps.b_hi = BN == 64 && c.bn == 128 ? c.map_bhi64 : c.map_bhi;
+    maps.b_lo = BN == 64 && c.bn == 128 ? c.map_blo64 : c.map_blo;
+    const uint64_t dims[4] = {(uint64_t)c.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)c.cin * 4, (uint64_t)W * c.cin * 4, (uint64_t)H * W * c.cin * 4};
+    const uint32_t box[4] = {(uint32_t)kTcBK, (uint32_t)(kTcTW * c.stride), (uint32_t)(kTcTH * c.stride), 1};
+    const uint32_t estr[4] = {1, (uint32_t)c.stride, (uint32_t)c.stride, 1};
+    int rc = make_tensor_map(&maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, estr);
+    if (rc) return rc;
+    TcArgs a;
+    a.bias = c.bias; a.residual = residual; a.out = out;
+    a.B = B; a.Ho = Ho; a.Wo = Wo; a.Cout = c.cout; a.Cin = c.cin; a.ksize = c.k; a.stride = c.stride; a.pad = c.pad;
+    a.relu = relu ? 1 : 0;
+    a.tiles_x = (Wo + kTcTW - 1) / kTcTW;
+    a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
+    a.mode = 0;
+    const long long total = (long long)a.tiles_x * a.tiles_y * B * (c.cout / BN);
+    const unsigned grid = (unsigned)(total < n_sm ? total : n_sm);
+    conv_tc_persist_kernel<BN><<<grid, kTcPersistThreads, TcPersistCfg<BN>::kSmem, st>>>(maps, a);
+    IRN_LAUNCH_CHECK("conv_tc_persist_kernel");
+    return kOk;
+}
+
 static int run_conv(const irn_net* net, const Conv& c, const float* in, int B, int H, int W, const float* residual, float* out, bool relu,
                     cudaStream_t st, int* Ho_, int* Wo_) {
     ConvGeom g;
@@ -294,6 +330,11 @@ static int run_conv(const irn_net* net, const Conv& c, const float* in, int B, i
         // short reductions (K <= 256) are latency-bound per tile: 64-wide tiles with a 2-stage pipeline and two TMEM
         // accumulators let two CTAs share an SM; long reductions use the 3-stage, 3-accumulator configuration
         const int K = c.k * c.k * c.cin;
+        static const int persist_max_k = getenv("IRN_TC_PERSIST_MAXK") ? atoi(getenv("IRN_TC_PERSIST_MAXK")) : 640;
+        if (K <= persist_max_k) {   // persistent, epilogue-overlapped kernel for the short reductions
+            if (c.bn == 128) return launch_tc_persist<128>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
+            return launch_tc_persist<64>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
+        }
         if (K <= 128) return launch_tc<64, 2, 2>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
         if (K <= 256) return launch_tc<64, 2, 3>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
         if (c.bn == 128) return launch_tc<128, 3, 3>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);

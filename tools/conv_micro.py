@@ -17,6 +17,9 @@ LAYERS = [  # name, cin, cout, k, stride, H(in), B, residual
     ("L4 c1 2048->512", 2048, 512, 1, 1, 64, 16, False),
 ]
 dev = torch.device("cuda:0")
+only = os.environ.get("CONV_ONLY")
+if only:
+    LAYERS = [l for l in LAYERS if only in l[0]]
 for name, cin, cout, k, s, H, B, res in LAYERS:
     w = (torch.randn(cout, cin, k, k) * (2.0 / (cin * k * k)) ** 0.5).numpy()
     bn = [np.ones(cout, np.float32), np.zeros(cout, np.float32), np.zeros(cout, np.float32), np.ones(cout, np.float32)]
