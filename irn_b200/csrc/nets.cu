@@ -22,11 +22,12 @@ struct Conv {
     int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
     float* wt = nullptr;     // device [k*k*cin][cout]   (SIMT kernel)
     float* bias = nullptr;   // device [cout] or null
-    // tensor-core path: weights [cout][k*k*cin] fp32 (split into tf32 hi / lo parts inside the kernel)
-    float* w_nk = nullptr;
+    // tensor-core path: weights [cout][k*k*cin] split into tf32 hi / lo parts
+    float* w_hi = nullptr;
+    float* w_lo = nullptr;
     int bn = 0;              // N tile (64 or 128); 0 = not eligible
-    CUtensorMap map_b;       // box {32, bn}
-    CUtensorMap map_b64;     // box {32, 64}
+    CUtensorMap map_bhi, map_blo;        // box {32, bn}
+    CUtensorMap map_bhi64, map_blo64;    // box {32, 64} (short-K configuration)
     bool stem_tc = false;    // 7x7/s2 stem repacked as 7 k-blocks of (8 taps x 4 channels) over a zero-haloed NHWC4 input
 };
 
@@ -124,16 +125,30 @@ static int read_conv(irn_net* net, Reader& rd, Conv& c, int cin, int cout, int k
     if (cin % kTcBK != 0 || !(k == 1 || k == 3) || !(stride == 1 || stride == 2)) c.bn = 0;
     if (c.bn) {
         const size_t K = (size_t)k * k * cin;
-        std::vector<float> nk(nw);
+        std::vector<float> hi(nw), lo(nw);
         for (int o = 0; o < cout; ++o)
-            for (size_t kk = 0; kk < K; ++kk) nk[(size_t)o * K + kk] = wt[kk * cout + o];
-        if ((rc = upload(net, nk, &c.w_nk))) return rc;
+            for (size_t kk = 0; kk < K; ++kk) {
+                const float v = wt[kk * cout + o];
+                uint32_t u;
+                std::memcpy(&u, &v, 4);
+                // round-to-nearest (ties away) to 10 explicit mantissa bits, like cvt.rna.tf32.f32
+                uint32_t h = (u + 0x1000u) & 0xFFFFE000u;
+                float hf;
+                std::memcpy(&hf, &h, 4);
+                if (!std::isfinite(hf)) hf = v;
+                hi[(size_t)o * K + kk] = hf;
+                lo[(size_t)o * K + kk] = v - hf;
+            }
+        if ((rc = upload(net, hi, &c.w_hi))) return rc;
+        if ((rc = upload(net, lo, &c.w_lo))) return rc;
         const uint64_t dims[2] = {(uint64_t)K, (uint64_t)cout};
         const uint64_t strides[1] = {(uint64_t)K * sizeof(float)};
         const uint32_t box[2] = {(uint32_t)kTcBK, (uint32_t)c.bn};
-        if ((rc = make_tensor_map(&c.map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_nk, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tensor_map(&c.map_bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tensor_map(&c.map_blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
         const uint32_t box64[2] = {(uint32_t)kTcBK, 64};
-        if ((rc = make_tensor_map(&c.map_b64, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_nk, dims, strides, box64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tensor_map(&c.map_bhi64, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_hi, dims, strides, box64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tensor_map(&c.map_blo64, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_lo, dims, strides, box64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     }
     return kOk;
 }
@@ -152,16 +167,28 @@ static int read_trunk(irn_net* net, Reader& rd) {
         std::vector<float> host((size_t)49 * 3 * 64);
         IRN_CUDA(cudaMemcpy(host.data(), c.wt, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
         const size_t K = 224;
-        std::vector<float> nk(64 * K, 0.f);
+        std::vector<float> hi(64 * K, 0.f), lo(64 * K, 0.f);
         for (int o = 0; o < 64; ++o)
             for (int r = 0; r < 7; ++r)
                 for (int t = 0; t < 7; ++t)
-                    for (int ci = 0; ci < 3; ++ci) nk[(size_t)o * K + r * 32 + t * 4 + ci] = host[((size_t)(r * 7 + t) * 3 + ci) * 64 + o];
-        if ((rc = upload(net, nk, &c.w_nk))) return rc;
+                    for (int ci = 0; ci < 3; ++ci) {
+                        const float v = host[((size_t)(r * 7 + t) * 3 + ci) * 64 + o];
+                        uint32_t u;
+                        std::memcpy(&u, &v, 4);
+                        uint32_t h = (u + 0x1000u) & 0xFFFFE000u;
+                        float hf;
+                        std::memcpy(&hf, &h, 4);
+                        if (!std::isfinite(hf)) hf = v;
+                        hi[(size_t)o * K + r * 32 + t * 4 + ci] = hf;
+                        lo[(size_t)o * K + r * 32 + t * 4 + ci] = v - hf;
+                    }
+        if ((rc = upload(net, hi, &c.w_hi))) return rc;
+        if ((rc = upload(net, lo, &c.w_lo))) return rc;
         const uint64_t dims[2] = {K, 64};
         const uint64_t strides[1] = {K * sizeof(float)};
         const uint32_t box[2] = {(uint32_t)kTcBK, 64};
-        if ((rc = make_tensor_map(&c.map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_nk, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tensor_map(&c.map_bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tensor_map(&c.map_blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
         c.stem_tc = true;
     }
     int cin = 64;
@@ -202,7 +229,8 @@ static int launch_tc(const Conv& c, const float* in, int B, int H, int W, int Ho
         attr_set = true;
     }
     TcMaps maps;
-    maps.b = BN == 64 && c.bn == 128 ? c.map_b64 : c.map_b;
+    maps.b_hi = BN == 64 && c.bn == 128 ? c.map_bhi64 : c.map_bhi;
+    maps.b_lo = BN == 64 && c.bn == 128 ? c.map_blo64 : c.map_blo;
     const uint64_t dims[4] = {(uint64_t)c.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)c.cin * 4, (uint64_t)W * c.cin * 4, (uint64_t)H * W * c.cin * 4};
     const uint32_t box[4] = {(uint32_t)kTcBK, (uint32_t)(kTcTW * c.stride), (uint32_t)(kTcTH * c.stride), 1};
@@ -232,7 +260,8 @@ static int launch_tc_stem(const Conv& c, const float* x4, int B, int Hin, int Wi
     const int Hp = Hin + 6, Wp = Win + 8;
     const int Ho = conv_out(Hin, 7, 2, 3), Wo = conv_out(Win, 7, 2, 3);
     TcMaps maps;
-    maps.b = c.map_b;
+    maps.b_hi = c.map_bhi;
+    maps.b_lo = c.map_blo;
     // dim0: the 32 contiguous floats (8 px x 4 ch) of one filter-row window; dim1: output column (windows overlap: stride 2 px = 32 B);
     // dim2: padded input row; dim3: image
     const uint64_t dims[4] = {32, (uint64_t)Wo, (uint64_t)Hp, (uint64_t)B};
@@ -266,7 +295,8 @@ static int launch_tc_persist(const Conv& c, const float* in, int B, int H, int W
         attr_set = true;
     }
     TcMaps maps;
-    maps.b = BN == 64 && c.bn == 128 ? c.map_b64 : c.map_b;
+    maps.b_hi = BN == 64 && c.bn == 128 ? c.map_bhi64 : c.map_bhi;
+    maps.b_lo = BN == 64 && c.bn == 128 ? c.map_blo64 : c.map_blo;
     const uint64_t dims[4] = {(uint64_t)c.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)c.cin * 4, (uint64_t)W * c.cin * 4, (uint64_t)H * W * c.cin * 4};
     const uint32_t box[4] = {(uint32_t)kTcBK, (uint32_t)(kTcTW * c.stride), (uint32_t)(kTcTH * c.stride), 1};
