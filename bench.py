@@ -199,7 +199,7 @@ def main():
     cam.cuda(dev), irn.cuda(dev)
     for m in (cam, irn):
         _lib.check(L.irn_net_set_conv_mode(m._get_plan(dev).handle, a.conv_mode))
-    pipe = PseudoLabelPipeline(cam, irn, dev, SCALES, rw_sub_batch=24)
+    pipe = PseudoLabelPipeline(cam, irn, dev, SCALES, rw_sub_batch=32)
 
     # ---- synthetic inputs: rank r takes images r, r+N, ... of the global list (misc/torchutils.py:66-68)
     B = a.batch

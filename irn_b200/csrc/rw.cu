@@ -298,12 +298,7 @@ rw_step_tma_kernel(const __grid_constant__ RwMaps maps, const double* __restrict
             tma_load_3d(s_w, &maps.w[0], &bars[1], x0 - kR, y0 - kR, img * 34 + cls_base5(0));
             mbar_arrive_expect_tx(&bars[2], (uint32_t)((cls_base5(2) - cls_base5(1)) * kWH * kSW * sizeof(float)));
             tma_load_3d(s_w + kWBufFloats, &maps.w[1], &bars[2], x0 - kR, y0 - kR, img * 34 + cls_base5(1));
-#ifndef IRN_RW_NO_L2_PREFETCH
-            // the remaining classes are loaded only when a buffer frees up: pull them into L2 now so those loads see L2 latency
-            tma_prefetch_3d(&maps.w[2], x0 - kR, y0 - kR, img * 34 + cls_base5(2));
-            tma_prefetch_3d(&maps.w[3], x0 - kR, y0 - kR, img * 34 + cls_base5(3));
-            tma_prefetch_3d(&maps.w[4], x0 - kR, y0 - kR, img * 34 + cls_base5(4));
-#endif
+            // (an L2 tensor prefetch of classes 2..4 at this point was measured 8 % SLOWER: 54.3 vs 50.2 us/step at C=2)
         }
         mbar_wait(&bars[0], ph_y);
         ph_y ^= 1;
