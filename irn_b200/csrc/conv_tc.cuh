@@ -529,4 +529,228 @@ conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// TS variant for the long reductions: the A operand is read from TENSOR MEMORY instead of shared memory.
+// Why: in SS mode a 128x128x8 tf32 MMA reads 8 KB of operands from shared memory in its 64-cycle slot = the SM's whole
+// 128 B/clk shared-memory bandwidth; the TMA writes (48 KB per k-block) and the hi/lo split (16 KB read + 32 KB written)
+// come on top: 192 KB per k-block ~ 1500 cycles against 768 cycles of tensor time (ncu: tensor pipe 58 % active).
+// Here the split warps read each activation row once from the (swizzled) TMA tile, and write A_hi / A_lo straight into
+// TMEM with tcgen05.st; the MMAs take A from TMEM and only B from shared memory: 112 KB of shared traffic per k-block.
+//   TMEM columns: [0,384) three accumulators (hi*hi even/odd k-blocks, cross terms); [384,512) two A slots x (hi 32 | lo 32)
+constexpr int kTsStages = 4;
+constexpr int kTsStageBytes = 16384 + 2 * 128 * 128;      // A raw | B_hi | B_lo
+constexpr size_t kTsSmem = 1024 + (size_t)kTsStages * kTsStageBytes + 256;
+
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+          "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+          "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
+    constexpr int BN = 128;
+    constexpr int S = kTsStages;
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    unsigned char* smem = tc_smem_raw;
+    uint64_t* bars = (uint64_t*)(smem + S * kTsStageBytes);
+    uint64_t* full = bars;                 // [S] TMA landed
+    uint64_t* split = bars + S;            // [S] A_hi / A_lo of this k-block are in TMEM
+    uint64_t* empty = bars + 2 * S;        // [S] MMAs finished reading the stage's B tiles
+    uint64_t* a_free = bars + 3 * S;       // [2] MMAs finished reading TMEM A slot
+    uint64_t* acc_full = bars + 3 * S + 2;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 3 * S + 3);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = args.Cout / BN;
+    const int tile = blockIdx.x / n_tiles;
+    const int tx = tile % args.tiles_x;
+    const int ty = (tile / args.tiles_x) % args.tiles_y;
+    const int b = tile / (args.tiles_x * args.tiles_y);
+    const int ox0 = tx * kTcTW, oy0 = ty * kTcTH;
+    const int n0 = (blockIdx.x % n_tiles) * BN;
+    const int cblocks = args.Cin / kTcBK;
+    const int KB = args.ksize * args.ksize * cblocks;
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) __trap();
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split[s], 4);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&a_free[0], 1);
+        mbar_init(&a_free[1], 1);
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t kAcol = 384;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&maps.a);
+            tma_prefetch_desc(&maps.b_hi);
+            tma_prefetch_desc(&maps.b_lo);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % S, it = kb / S;
+                mbar_wait(&empty[s], (it & 1) ^ 1);
+                unsigned char* st = smem + s * kTsStageBytes;
+                const int tap = kb / cblocks, cb = kb % cblocks;
+                const int r = tap / args.ksize, ss = tap % args.ksize;
+                mbar_arrive_expect_tx(&full[s], 16384u + 2u * BN * 128u);
+                tma_load_4d(st, &maps.a, &full[s], cb * kTcBK, ox0 * args.stride - args.pad + ss, oy0 * args.stride - args.pad + r, b);
+                tma_load_2d(st + 16384, &maps.b_hi, &full[s], kb * kTcBK, n0);
+                tma_load_2d(st + 16384 + BN * 128, &maps.b_lo, &full[s], kb * kTcBK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc(128, BN);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % S, it = kb / S;
+                mbar_wait(&full[s], it & 1);
+                mbar_wait(&split[s], it & 1);
+                tc_fence_after();
+                const uint32_t b_hi = smem_u32(smem + s * kTsStageBytes + 16384), b_lo = b_hi + BN * 128;
+                const uint32_t a_t = tmem_base + kAcol + (uint32_t)(kb & 1) * 64u;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const uint64_t db_hi = tc_smem_desc(b_hi + k4 * 32), db_lo = tc_smem_desc(b_lo + k4 * 32);
+                    const uint32_t ta_hi = a_t + k4 * 8, ta_lo = a_t + 32 + k4 * 8;
+                    tc_mma_tf32_ts(tmem_base + (uint32_t)((kb & 1) * BN), ta_hi, db_hi, idesc, (kb >= 2 || k4 != 0) ? 1u : 0u);
+                    tc_mma_tf32_ts(tmem_base + 2u * BN, ta_lo, db_hi, idesc, (kb | k4) != 0);
+                    tc_mma_tf32_ts(tmem_base + 2u * BN, ta_hi, db_lo, idesc, 1);
+                }
+                tc_commit(&empty[s]);
+                tc_commit(&a_free[kb & 1]);
+            }
+            tc_commit(acc_full);
+        }
+    } else {
+        // ---- split warps: thread = tile row (TMEM lane), one 128-byte row of the swizzled TMA tile per k-block
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % S, it = kb / S;
+            const int slot = kb & 1;
+            mbar_wait(&full[s], it & 1);
+            const float4* arow = reinterpret_cast<const float4*>(smem + s * kTsStageBytes + row * 128);
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 v = arow[c ^ (row & 7)];      // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r % 8)
+                const float h0 = rna_tf32(v.x), h1 = rna_tf32(v.y), h2 = rna_tf32(v.z), h3 = rna_tf32(v.w);
+                hi[4 * c] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1); hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
+                lo[4 * c] = __float_as_uint(rna_tf32(v.x - h0)); lo[4 * c + 1] = __float_as_uint(rna_tf32(v.y - h1));
+                lo[4 * c + 2] = __float_as_uint(rna_tf32(v.z - h2)); lo[4 * c + 3] = __float_as_uint(rna_tf32(v.w - h3));
+            }
+            mbar_wait(&a_free[slot], ((kb >> 1) & 1) ^ 1);    // the MMAs of k-block kb-2 released this TMEM slot
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kAcol + (uint32_t)slot * 64u;
+            tc_st32(taddr, hi);
+            tc_st32(taddr + 32, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&split[s]);
+        }
+        // ---- epilogue (same as conv_tc_kernel: TMEM -> shared staging -> coalesced stores, residual rows prefetched)
+        constexpr int kLd = BN + 4;
+        constexpr int kRB = 16;
+        const int col = lane * 4;
+        float* stg = reinterpret_cast<float*>(smem) + (size_t)q * 32 * kLd;
+        float4 res[kRB];
+        auto row_offset = [&](int it, bool& ok) -> size_t {
+            const int rr = q * 32 + it;
+            const int oy = oy0 + rr / kTcTW, ox = ox0 + rr % kTcTW;
+            ok = oy < args.Ho && ox < args.Wo;
+            return (((size_t)b * args.Ho + oy) * args.Wo + ox) * args.Cout + n0 + col;
+        };
+        auto prefetch = [&](int base) {
+#pragma unroll
+            for (int i = 0; i < kRB; ++i) {
+                bool ok;
+                const size_t off = row_offset(base + i, ok);
+                res[i] = (ok && args.residual) ? __ldg(reinterpret_cast<const float4*>(args.residual + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        prefetch(0);
+        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (args.bias) bi = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + col));
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; ++cc) {
+            uint32_t v[32], u[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
+            tc_ld32(taddr, v);
+            tc_ld32(taddr + 2u * BN, u);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (KB >= 2) {
+                uint32_t t2[32];
+                tc_ld32(taddr + (uint32_t)BN, t2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t2[j]));
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 o;
+                o.x = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                o.y = __uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1]);
+                o.z = __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]);
+                o.w = __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3]);
+                *reinterpret_cast<float4*>(stg + lane * kLd + cc * 32 + j) = o;
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int base = 0; base < 32; base += kRB) {
+            if (base > 0) prefetch(base);
+#pragma unroll
+            for (int i = 0; i < kRB; ++i) {
+                bool ok;
+                const size_t off = row_offset(base + i, ok);
+                if (ok) {
+                    float4 o = *reinterpret_cast<const float4*>(stg + (base + i) * kLd + col);
+                    o.x += bi.x + res[i].x; o.y += bi.y + res[i].y; o.z += bi.z + res[i].z; o.w += bi.w + res[i].w;
+                    if (args.relu) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    }
+                    *reinterpret_cast<float4*>(args.out + off) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
 }  // namespace irn

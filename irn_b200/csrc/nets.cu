@@ -317,6 +317,35 @@ static int launch_tc_persist(const Conv& c, const float* in, int B, int H, int W
     return kOk;
 }
 
+static int launch_tc_ts(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
+                        cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        IRN_CUDA(cudaFuncSetAttribute(conv_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTsSmem));
+        attr_set = true;
+    }
+    TcMaps maps;
+    maps.b_hi = c.map_bhi;
+    maps.b_lo = c.map_blo;
+    const uint64_t dims[4] = {(uint64_t)c.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)c.cin * 4, (uint64_t)W * c.cin * 4, (uint64_t)H * W * c.cin * 4};
+    const uint32_t box[4] = {(uint32_t)kTcBK, (uint32_t)(kTcTW * c.stride), (uint32_t)(kTcTH * c.stride), 1};
+    const uint32_t estr[4] = {1, (uint32_t)c.stride, (uint32_t)c.stride, 1};
+    int rc = make_tensor_map(&maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, estr);
+    if (rc) return rc;
+    TcArgs a;
+    a.bias = c.bias; a.residual = residual; a.out = out;
+    a.B = B; a.Ho = Ho; a.Wo = Wo; a.Cout = c.cout; a.Cin = c.cin; a.ksize = c.k; a.stride = c.stride; a.pad = c.pad;
+    a.relu = relu ? 1 : 0;
+    a.tiles_x = (Wo + kTcTW - 1) / kTcTW;
+    a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
+    a.mode = 0;
+    dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B * (c.cout / 128)));
+    conv_tc_ts_kernel<<<grid, kTcThreads, kTsSmem, st>>>(maps, a);
+    IRN_LAUNCH_CHECK("conv_tc_ts_kernel");
+    return kOk;
+}
+
 static int run_conv(const irn_net* net, const Conv& c, const float* in, int B, int H, int W, const float* residual, float* out, bool relu,
                     cudaStream_t st, int* Ho_, int* Wo_) {
     ConvGeom g;
@@ -337,6 +366,8 @@ static int run_conv(const irn_net* net, const Conv& c, const float* in, int B, i
         }
         if (K <= 128) return launch_tc<64, 2, 2>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
         if (K <= 256) return launch_tc<64, 2, 3>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
+        static const int use_ts = getenv("IRN_TC_TS") ? atoi(getenv("IRN_TC_TS")) : 1;
+        if (c.bn == 128 && use_ts) return launch_tc_ts(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);   // A operand from TMEM
         if (c.bn == 128) return launch_tc<128, 3, 3>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
         return launch_tc<64, 3, 3>(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
     }

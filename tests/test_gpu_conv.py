@@ -15,6 +15,9 @@ CASES = [  # cin, cout, k, stride, pad, B, H, W
     (128, 128, 3, 2, 1, 2, 64, 64),
     (256, 512, 1, 2, 0, 2, 33, 47),
     (512, 128, 1, 1, 0, 3, 16, 16),
+    (512, 512, 3, 1, 1, 2, 20, 24),    # K = 4608: A-from-TMEM kernel
+    (1024, 256, 1, 1, 0, 2, 33, 17),
+    (2048, 512, 1, 1, 0, 1, 16, 16),
     (3, 64, 7, 2, 3, 2, 64, 80),       # stem: SIMT only
     (2048, 32, 1, 1, 0, 2, 8, 8),      # edge head: SIMT only
 ]
