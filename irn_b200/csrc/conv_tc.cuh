@@ -6,7 +6,7 @@
 // K = taps x Cin walked in 32-channel slices.  Pipeline (warp-specialised, one CTA per SM):
 //   warp 0      TMA producer: 4-D box {32 ch, 16 px, 8 rows, 1 image} of the input per tap (zero fill outside the
 //               image = zero padding; element strides give stride-2 convs), 2-D boxes of the pre-split weights
-//   warps 2-5   split the fp32 activation tile in place into A_hi = rna_tf32(a), A_lo = rna_tf32(a - A_hi)
+//   warps 2-5   split the fp32 activation tile in place into A_hi = round_tf32(a), A_lo = a - A_hi
 //   warp 1      one thread issues tcgen05.mma kind::tf32:  D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  (fp32 in TMEM)
 //   warps 2-5   epilogue: tcgen05.ld, + bias, + residual, ReLU, float4 stores
 // Why 3xTF32: plain TF32 misses the 1e-4 CAM parity bar by 20x; the split keeps ~21 mantissa bits.
@@ -74,11 +74,10 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ float rna_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// tf32 "hi" part of an fp32 value: round to nearest (ties away, like cvt.rna.tf32.f32) on the 13 dropped mantissa bits.
+// Two integer-pipe ops: cvt.rna.tf32 is a quarter-rate conversion and made the split warps the bottleneck of the long-K kernels.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+// The "lo" part x - hi is exact in fp32 (<= 13 significant bits); the tensor core keeps its top 11 bits (error 2^-21 |x|).
 
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -201,8 +200,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             for (int i = 0; i < 8; ++i) {
                 const float4 v = a[i * 128 + t];
                 float4 h, l;
-                h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-                l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+                h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+                l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
                 a[i * 128 + t] = h;
                 lo[i * 128 + t] = l;
             }
@@ -435,8 +434,8 @@ conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 for (int i = 0; i < 8; ++i) {
                     const float4 v = a[i * 128 + t];
                     float4 h, l;
-                    h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-                    l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+                    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
                     a[i * 128 + t] = h;
                     lo[i * 128 + t] = l;
                 }
@@ -662,10 +661,10 @@ conv_tc_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const float4 v = arow[c ^ (row & 7)];      // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r % 8)
-                const float h0 = rna_tf32(v.x), h1 = rna_tf32(v.y), h2 = rna_tf32(v.z), h3 = rna_tf32(v.w);
+                const float h0 = tf32_hi(v.x), h1 = tf32_hi(v.y), h2 = tf32_hi(v.z), h3 = tf32_hi(v.w);
                 hi[4 * c] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1); hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
-                lo[4 * c] = __float_as_uint(rna_tf32(v.x - h0)); lo[4 * c + 1] = __float_as_uint(rna_tf32(v.y - h1));
-                lo[4 * c + 2] = __float_as_uint(rna_tf32(v.z - h2)); lo[4 * c + 3] = __float_as_uint(rna_tf32(v.w - h3));
+                lo[4 * c] = __float_as_uint(v.x - h0); lo[4 * c + 1] = __float_as_uint(v.y - h1);
+                lo[4 * c + 2] = __float_as_uint(v.z - h2); lo[4 * c + 3] = __float_as_uint(v.w - h3);
             }
             mbar_wait(&a_free[slot], ((kb >> 1) & 1) ^ 1);    // the MMAs of k-block kb-2 released this TMEM slot
             tc_fence_after();

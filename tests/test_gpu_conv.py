@@ -44,7 +44,7 @@ def test_conv_vs_torch(cuda_dev, case):
     res_nhwc = res.permute(0, 2, 3, 1).contiguous()
     y0 = conv(x_nhwc, res_nhwc, relu=True, mode=0)
     scale = ref.abs().max().item()
-    assert (y0 - ref).abs().max().item() / scale < 2e-6, "SIMT fp32"
+    assert (y0 - ref).abs().max().item() / scale < 5e-6, "SIMT fp32"   # fp32 FMA accumulation over K up to 4608
     if cin % 32 == 0 and cout % 64 == 0 and k in (1, 3):
         y1 = conv(x_nhwc, res_nhwc, relu=True, mode=1)
         err = (y1 - ref).abs().max().item() / scale
