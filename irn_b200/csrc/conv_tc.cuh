@@ -552,6 +552,15 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32])
         : "memory");
 }
 
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -561,7 +570,9 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a,
         : "memory");
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+constexpr int kTsThreads = 320;   // TMA + MMA warps, 8 split warps (two per TMEM lane quarter); the first four also run the epilogue
+
+__global__ void __launch_bounds__(kTsThreads, 1)
 conv_tc_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     constexpr int BN = 128;
     constexpr int S = kTsStages;
@@ -590,7 +601,7 @@ conv_tc_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&split[s], 4);
+            mbar_init(&split[s], 8);
             mbar_init(&empty[s], 1);
         }
         mbar_init(&a_free[0], 1);
@@ -649,18 +660,20 @@ conv_tc_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             tc_commit(acc_full);
         }
     } else {
-        // ---- split warps: thread = tile row (TMEM lane), one 128-byte row of the swizzled TMA tile per k-block
+        // ---- split warps: thread = tile row (TMEM lane); warps 2-5 take the first 16 channels of the row's 128-byte slice of the
+        // swizzled TMA tile, warps 6-9 the other 16 (two warps per scheduler keep the LDS -> round -> STTM chain busy)
         const int q = warp & 3;
+        const int half = warp >= 6 ? 1 : 0;
         const int row = q * 32 + lane;
         for (int kb = 0; kb < KB; ++kb) {
             const int s = kb % S, it = kb / S;
             const int slot = kb & 1;
             mbar_wait(&full[s], it & 1);
             const float4* arow = reinterpret_cast<const float4*>(smem + s * kTsStageBytes + row * 128);
-            uint32_t hi[32], lo[32];
+            uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 v = arow[c ^ (row & 7)];      // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r % 8)
+            for (int c = 0; c < 4; ++c) {
+                const float4 v = arow[(half * 4 + c) ^ (row & 7)];      // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r % 8)
                 const float h0 = tf32_hi(v.x), h1 = tf32_hi(v.y), h2 = tf32_hi(v.z), h3 = tf32_hi(v.w);
                 hi[4 * c] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1); hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
                 lo[4 * c] = __float_as_uint(v.x - h0); lo[4 * c + 1] = __float_as_uint(v.y - h1);
@@ -668,15 +681,16 @@ conv_tc_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             }
             mbar_wait(&a_free[slot], ((kb >> 1) & 1) ^ 1);    // the MMAs of k-block kb-2 released this TMEM slot
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kAcol + (uint32_t)slot * 64u;
-            tc_st32(taddr, hi);
-            tc_st32(taddr + 32, lo);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kAcol + (uint32_t)slot * 64u + (uint32_t)half * 16u;
+            tc_st16(taddr, hi);
+            tc_st16(taddr + 32, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[s]);
         }
-        // ---- epilogue (same as conv_tc_kernel: TMEM -> shared staging -> coalesced stores, residual rows prefetched)
+        if (warp < 6) {
+        // ---- epilogue on warps 2-5 (same as conv_tc_kernel: TMEM -> shared staging -> coalesced stores, residual rows prefetched)
         constexpr int kLd = BN + 4;
         constexpr int kRB = 16;
         const int col = lane * 4;
@@ -743,6 +757,7 @@ conv_tc_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 }
             }
         }
+        }   // warp < 6
     }
     tc_fence_before();
     __syncthreads();

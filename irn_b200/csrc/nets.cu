@@ -341,7 +341,7 @@ static int launch_tc_ts(const Conv& c, const float* in, int B, int H, int W, int
     a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
     a.mode = 0;
     dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B * (c.cout / 128)));
-    conv_tc_ts_kernel<<<grid, kTcThreads, kTsSmem, st>>>(maps, a);
+    conv_tc_ts_kernel<<<grid, kTsThreads, kTsSmem, st>>>(maps, a);
     IRN_LAUNCH_CHECK("conv_tc_ts_kernel");
     return kOk;
 }
