@@ -1,6 +1,19 @@
-"""Shared plumbing of the three label-generation steps: collation, progress printing, process spawn."""
+"""Shared plumbing of the three label-generation steps.
+
+The reference repeats the same skeleton in step/make_cam.py, step/make_sem_seg_labels.py and
+step/make_ins_seg_labels.py: build the model class named on the command line, load its checkpoint, split the
+image list over the visible GPUs with the stride partition, spawn one worker per GPU, loop over a batch-size-1
+DataLoader.  Here that skeleton exists once; each step module only supplies its per-image function.
+"""
+import importlib
+import os
+
 import torch
+from torch.utils.data import DataLoader
 from torch.utils.data._utils.collate import default_collate
+
+from ..misc import torchutils
+from ..voc12 import dataloader as voc_data
 
 
 def collate_one(batch):
@@ -20,12 +33,41 @@ def progress(process_id, n_gpus, it, n_items):
         print("%d " % ((5 * it + 1) // step), end="", flush=True)
 
 
-def spawn(work, n_gpus, args_tuple):
-    """One process per GPU like the reference (multiprocessing.spawn, step/make_cam.py:74); a single visible GPU
-    runs in-process."""
+def make_dataset(args, list_path, scales):
+    """VOC images from --voc12_root, or seeded synthetic ones with --synthetic N."""
+    if getattr(args, "synthetic", 0):
+        names = list_path if os.path.exists(list_path) else None
+        return voc_data.SyntheticMSF(int(args.synthetic), scales=scales, name_list=names)
+    return voc_data.VOC12ClassificationDatasetMSF(list_path, voc12_root=args.voc12_root, scales=scales)
+
+
+def work_loop(process_id, model, dataset, args, per_image):
+    """One GPU's share: the reference's `_work(process_id, model, dataset, args)` signature and loop order
+    (step/make_cam.py:16-59), with the per-image body supplied by the step."""
+    shard = dataset[process_id]
+    n_gpus = torch.cuda.device_count()
+    loader = DataLoader(shard, shuffle=False, num_workers=args.num_workers // max(n_gpus, 1), pin_memory=False, collate_fn=collate_one)
+    with torch.no_grad(), torch.cuda.device(process_id):
+        model.cuda()
+        for it, pack in enumerate(loader):
+            per_image(model, pack, args)
+            progress(process_id, n_gpus, it, len(shard))
+
+
+def run_step(args, work, module_name, class_name, weights_path, strict, list_path, scales, opening="[ "):
+    """The reference's `run(args)` (e.g. step/make_cam.py:62-77): model class resolved by name, checkpoint loaded,
+    stride partition (misc/torchutils.py:66-68), one process per GPU (a single GPU runs in-process)."""
+    model = getattr(importlib.import_module(module_name), class_name)()
+    model.load_state_dict(torch.load(weights_path), strict=strict)
+    model.eval()
+    n_gpus = torch.cuda.device_count()
     if n_gpus <= 0:
         raise RuntimeError("irn_b200 steps need at least one CUDA device (there is no CPU fallback)")
+    shards = torchutils.split_dataset(make_dataset(args, list_path, scales), n_gpus)
+    print(opening, end="")
     if n_gpus == 1:
-        work(0, *args_tuple)
+        work(0, model, shards, args)
     else:
-        torch.multiprocessing.spawn(work, nprocs=n_gpus, args=args_tuple, join=True)
+        torch.multiprocessing.spawn(work, nprocs=n_gpus, args=(model, shards, args), join=True)
+    print("]")
+    torch.cuda.empty_cache()
