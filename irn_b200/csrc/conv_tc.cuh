@@ -767,4 +767,231 @@ conv_tc_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     }
 }
 
+// ---- 2-CTA cluster helpers (weight tile multicast)
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+// Same as conv_tc_ts_kernel, in CTA pairs: the L2 -> SM operand feed (48 KB per k-block per SM, 6.2 KB/clk chip-wide = the L2
+// slice limit) was the binding constraint of the long-K layers once the A operand moved to TMEM; sharing the weight tile
+// between two M tiles cuts it to 32 KB.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTsThreads, 1)
+conv_tc_ts2_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
+    constexpr int BN = 128;
+    constexpr int S = kTsStages;
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    unsigned char* smem = tc_smem_raw;
+    uint64_t* bars = (uint64_t*)(smem + S * kTsStageBytes);
+    uint64_t* full = bars;                 // [S] TMA landed
+    uint64_t* split = bars + S;            // [S] A_hi / A_lo of this k-block are in TMEM
+    uint64_t* empty = bars + 2 * S;        // [S] MMAs finished reading the stage's B tiles
+    uint64_t* a_free = bars + 3 * S;       // [2] MMAs finished reading TMEM A slot
+    uint64_t* acc_full = bars + 3 * S + 2;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 3 * S + 3);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // CTA pair = two consecutive M tiles of the same N tile: each CTA fetches half of the weight tile and multicasts it to both
+    const uint32_t rank = cluster_rank();
+    const int n_tiles = args.Cout / BN;
+    const int pair = blockIdx.x >> 1;
+    const int m_tiles = args.tiles_x * args.tiles_y * args.B;
+    const int tile = (pair / n_tiles) * 2 + (int)rank;
+    const bool ghost = tile >= m_tiles;            // odd tile count: the partner of the last tile computes on zero-filled input, stores nothing
+    const int tx = tile % args.tiles_x;
+    const int ty = (tile / args.tiles_x) % args.tiles_y;
+    const int b = tile / (args.tiles_x * args.tiles_y);   // == args.B for the ghost: TMA zero-fills
+    const int ox0 = tx * kTcTW, oy0 = ty * kTcTH;
+    const int n0 = (pair % n_tiles) * BN;
+    const int cblocks = args.Cin / kTcBK;
+    const int KB = args.ksize * args.ksize * cblocks;
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) __trap();
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split[s], 8);
+            mbar_init(&empty[s], 2);        // both CTAs of the pair must have finished with stage s before it is refilled
+        }
+        mbar_init(&a_free[0], 1);
+        mbar_init(&a_free[1], 1);
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                            // the peer's barriers exist before anything is multicast at them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t kAcol = 384;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&maps.a);
+            tma_prefetch_desc(&maps.b_hi);
+            tma_prefetch_desc(&maps.b_lo);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % S, it = kb / S;
+                mbar_wait(&empty[s], (it & 1) ^ 1);
+                unsigned char* st = smem + s * kTsStageBytes;
+                const int tap = kb / cblocks, cb = kb % cblocks;
+                const int r = tap / args.ksize, ss = tap % args.ksize;
+                mbar_arrive_expect_tx(&full[s], 16384u + 2u * BN * 128u);
+                tma_load_4d(st, &maps.a, &full[s], cb * kTcBK, ox0 * args.stride - args.pad + ss, oy0 * args.stride - args.pad + r, b);
+                // this CTA's 64 rows of the weight tile go to the same place in BOTH CTAs (and signal both full barriers)
+                tma_load_2d_mc(st + 16384 + rank * 8192, &maps.b_hi, &full[s], kb * kTcBK, n0 + (int)rank * 64, (uint16_t)3);
+                tma_load_2d_mc(st + 16384 + BN * 128 + rank * 8192, &maps.b_lo, &full[s], kb * kTcBK, n0 + (int)rank * 64, (uint16_t)3);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc(128, BN);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % S, it = kb / S;
+                mbar_wait(&full[s], it & 1);
+                mbar_wait(&split[s], it & 1);
+                tc_fence_after();
+                const uint32_t b_hi = smem_u32(smem + s * kTsStageBytes + 16384), b_lo = b_hi + BN * 128;
+                const uint32_t a_t = tmem_base + kAcol + (uint32_t)(kb & 1) * 64u;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const uint64_t db_hi = tc_smem_desc(b_hi + k4 * 32), db_lo = tc_smem_desc(b_lo + k4 * 32);
+                    const uint32_t ta_hi = a_t + k4 * 8, ta_lo = a_t + 32 + k4 * 8;
+                    tc_mma_tf32_ts(tmem_base + (uint32_t)((kb & 1) * BN), ta_hi, db_hi, idesc, (kb >= 2 || k4 != 0) ? 1u : 0u);
+                    tc_mma_tf32_ts(tmem_base + 2u * BN, ta_lo, db_hi, idesc, (kb | k4) != 0);
+                    tc_mma_tf32_ts(tmem_base + 2u * BN, ta_hi, db_lo, idesc, 1);
+                }
+                tc_commit_mc(&empty[s], (uint16_t)3);   // frees stage s in both CTAs
+                tc_commit(&a_free[kb & 1]);
+            }
+            tc_commit(acc_full);
+        }
+    } else {
+        // ---- split warps: thread = tile row (TMEM lane); warps 2-5 take the first 16 channels of the row's 128-byte slice of the
+        // swizzled TMA tile, warps 6-9 the other 16 (two warps per scheduler keep the LDS -> round -> STTM chain busy)
+        const int q = warp & 3;
+        const int half = warp >= 6 ? 1 : 0;
+        const int row = q * 32 + lane;
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % S, it = kb / S;
+            const int slot = kb & 1;
+            mbar_wait(&full[s], it & 1);
+            const float4* arow = reinterpret_cast<const float4*>(smem + s * kTsStageBytes + row * 128);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float4 v = arow[(half * 4 + c) ^ (row & 7)];      // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r % 8)
+                const float h0 = tf32_hi(v.x), h1 = tf32_hi(v.y), h2 = tf32_hi(v.z), h3 = tf32_hi(v.w);
+                hi[4 * c] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1); hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
+                lo[4 * c] = __float_as_uint(v.x - h0); lo[4 * c + 1] = __float_as_uint(v.y - h1);
+                lo[4 * c + 2] = __float_as_uint(v.z - h2); lo[4 * c + 3] = __float_as_uint(v.w - h3);
+            }
+            mbar_wait(&a_free[slot], ((kb >> 1) & 1) ^ 1);    // the MMAs of k-block kb-2 released this TMEM slot
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kAcol + (uint32_t)slot * 64u + (uint32_t)half * 16u;
+            tc_st16(taddr, hi);
+            tc_st16(taddr + 32, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&split[s]);
+        }
+        if (warp < 6) {
+        // ---- epilogue on warps 2-5 (same as conv_tc_kernel: TMEM -> shared staging -> coalesced stores, residual rows prefetched)
+        constexpr int kLd = BN + 4;
+        constexpr int kRB = 16;
+        const int col = lane * 4;
+        float* stg = reinterpret_cast<float*>(smem) + (size_t)q * 32 * kLd;
+        float4 res[kRB];
+        auto row_offset = [&](int it, bool& ok) -> size_t {
+            const int rr = q * 32 + it;
+            const int oy = oy0 + rr / kTcTW, ox = ox0 + rr % kTcTW;
+            ok = !ghost && oy < args.Ho && ox < args.Wo;
+            return (((size_t)b * args.Ho + oy) * args.Wo + ox) * args.Cout + n0 + col;
+        };
+        auto prefetch = [&](int base) {
+#pragma unroll
+            for (int i = 0; i < kRB; ++i) {
+                bool ok;
+                const size_t off = row_offset(base + i, ok);
+                res[i] = (ok && args.residual) ? __ldg(reinterpret_cast<const float4*>(args.residual + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        prefetch(0);
+        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (args.bias) bi = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + col));
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; ++cc) {
+            uint32_t v[32], u[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
+            tc_ld32(taddr, v);
+            tc_ld32(taddr + 2u * BN, u);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (KB >= 2) {
+                uint32_t t2[32];
+                tc_ld32(taddr + (uint32_t)BN, t2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t2[j]));
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 o;
+                o.x = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                o.y = __uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1]);
+                o.z = __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]);
+                o.w = __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3]);
+                *reinterpret_cast<float4*>(stg + lane * kLd + cc * 32 + j) = o;
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int base = 0; base < 32; base += kRB) {
+            if (base > 0) prefetch(base);
+#pragma unroll
+            for (int i = 0; i < kRB; ++i) {
+                bool ok;
+                const size_t off = row_offset(base + i, ok);
+                if (ok) {
+                    float4 o = *reinterpret_cast<const float4*>(stg + (base + i) * kLd + col);
+                    o.x += bi.x + res[i].x; o.y += bi.y + res[i].y; o.z += bi.z + res[i].z; o.w += bi.w + res[i].w;
+                    if (args.relu) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    }
+                    *reinterpret_cast<float4*>(args.out + off) = o;
+                }
+            }
+        }
+        }   // warp < 6
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                            // nobody exits while the peer may still write into its shared memory / barriers
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
+
 }  // namespace irn

@@ -340,6 +340,21 @@ static int launch_tc_ts(const Conv& c, const float* in, int B, int H, int W, int
     a.tiles_x = (Wo + kTcTW - 1) / kTcTW;
     a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
     a.mode = 0;
+    static const int use_pair = getenv("IRN_TC_PAIR") ? atoi(getenv("IRN_TC_PAIR")) : 1;
+    if (use_pair) {
+        static bool attr2 = false;
+        if (!attr2) {
+            IRN_CUDA(cudaFuncSetAttribute(conv_tc_ts2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTsSmem));
+            attr2 = true;
+        }
+        maps.b_hi = c.map_bhi64;    // each CTA of a pair loads 64 of the 128 weight rows and multicasts them
+        maps.b_lo = c.map_blo64;
+        const long long m_tiles = (long long)a.tiles_x * a.tiles_y * B;
+        dim3 grid2((unsigned)(((m_tiles + 1) / 2) * (c.cout / 128) * 2));
+        conv_tc_ts2_kernel<<<grid2, kTsThreads, kTsSmem, st>>>(maps, a);
+        IRN_LAUNCH_CHECK("conv_tc_ts2_kernel");
+        return kOk;
+    }
     dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B * (c.cout / 128)));
     conv_tc_ts_kernel<<<grid, kTsThreads, kTsSmem, st>>>(maps, a);
     IRN_LAUNCH_CHECK("conv_tc_ts_kernel");
