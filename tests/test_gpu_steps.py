@@ -86,3 +86,22 @@ def test_make_ins_seg_labels_outputs(voc_tree):
         a, b = paint(d["mask"], d["class"]), paint(ref_mask, g["ins_class%d" % i])
         assert (a != b).mean() < 1e-2
         assert sorted(set(np.asarray(d["class"]).tolist())) == sorted(set(g["ins_class%d" % i].tolist()))
+
+
+def test_run_sample_cli_synthetic(tmp_path, cuda_dev):
+    """`python run_sample.py --synthetic N` (reference flag names, default output dirs) writes the three result trees."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "run_sample.py"), "--synthetic", "2", "--num_workers", "0", "--exp_times", "6"],
+                       cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for i in range(2):
+        name = "2007_%06d" % i
+        d = np.load(tmp_path / "result" / "cam" / (name + ".npy"), allow_pickle=True).item()
+        assert d["cam"].shape[1:] == (128, 128) and d["high_res"].shape[1:] == (512, 512)
+        lab = np.asarray(Image.open(tmp_path / "result" / "sem_seg" / (name + ".png")))
+        assert lab.shape == (512, 512) and lab.dtype == np.uint8
+        ins = np.load(tmp_path / "result" / "ins_seg" / (name + ".npy"), allow_pickle=True).item()
+        assert set(ins) == {"score", "mask", "class"} and ins["mask"].shape[1:] == (512, 512)
