@@ -249,7 +249,7 @@ constexpr size_t rw_tma_smem_bytes(int ch) {
 
 struct RwMaps {
     CUtensorMap w[5];   // weights, one map per |dx| class (box depth = class size)
-    CUtensorMap y;      // state being read
+    CUtensorMap y[4];   // state being read, box depth 1..4 channels
 };
 
 // One walk step for CH channels of one 32x16 tile.  Thread = one column, kPY consecutive rows.
@@ -259,41 +259,20 @@ struct RwMaps {
 //   mirrored tap d=(j-r,-dxc):   weight W_d(p_j - d) = W_d at the very cell being read
 // The 34 weight planes stream through two shared-memory buffers one |dx| class at a time (TMA,
 // zero-filled outside the image, which is exactly the reference's "affinity 0 to anything outside").
+// One channel chunk (CH = 1..4 channels of one image) of one tile: issue the TMA loads, run the five |dx| classes, store.
 template <int CH>
-__global__ void __launch_bounds__(kTX* kWarps)
-rw_step_tma_kernel(const __grid_constant__ RwMaps maps, const double* __restrict__ inv_s, double* __restrict__ yout,
-                   const int* __restrict__ chan_off, int h, int w, int pitch) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];   // TMA destinations need 128-byte alignment
-    double* s_y = (double*)smem_raw;                                              // [CH][kYH][kSW]
-    float* s_w = (float*)(smem_raw + (size_t)CH * kYH * kSW * sizeof(double));   // [2][<=9][kWH][kSW]
-    uint64_t* bars = (uint64_t*)(s_w + 2 * kWBufFloats);                     // [0]=y, [1],[2]=weight buffers
-
+__device__ __forceinline__ void rw_chunk(const RwMaps& maps, const double* __restrict__ inv_s, double* __restrict__ yout, double* s_y,
+                                         float* s_w, uint64_t* bars, uint32_t& ph_y, uint32_t& ph_w0, uint32_t& ph_w1, int img, int c0,
+                                         int c_end, int x0, int y0, int h, int w, int pitch) {
     const int tid = threadIdx.x;
-    const int tiles_x = (w + kTX - 1) / kTX;
-    const int x0 = (blockIdx.x % tiles_x) * kTX, y0 = (blockIdx.x / tiles_x) * kTY;
-    const int img = blockIdx.y;
-    const int c_begin = chan_off[img], c_end = chan_off[img + 1];
-    if (c_begin >= c_end) return;
-
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        mbar_init(&bars[2], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-
     const int lane = tid & 31, warp = tid >> 5;
     const int x = x0 + lane;
     const int ty0 = warp * kPY;
     const int yb = y0 + ty0;
     const size_t plane_sz = (size_t)h * pitch;
-    uint32_t ph_y = 0, ph_w0 = 0, ph_w1 = 0;
-
-    for (int c0 = c_begin; c0 < c_end; c0 += CH) {
         if (tid == 0) {
             mbar_arrive_expect_tx(&bars[0], (uint32_t)(CH * kYH * kSW * sizeof(double)));
-            tma_load_3d(s_y, &maps.y, &bars[0], x0 - kR, y0 - kR, c0);
+            tma_load_3d(s_y, &maps.y[CH - 1], &bars[0], x0 - kR, y0 - kR, c0);
             mbar_arrive_expect_tx(&bars[1], (uint32_t)((cls_base5(1) - cls_base5(0)) * kWH * kSW * sizeof(float)));
             tma_load_3d(s_w, &maps.w[0], &bars[1], x0 - kR, y0 - kR, img * 34 + cls_base5(0));
             mbar_arrive_expect_tx(&bars[2], (uint32_t)((cls_base5(2) - cls_base5(1)) * kWH * kSW * sizeof(float)));
@@ -365,6 +344,42 @@ rw_step_tma_kernel(const __grid_constant__ RwMaps maps, const double* __restrict
                 }
             }
         }
+}
+
+// Grid (tiles, images).  MAXCH sizes the state buffer; every image is processed with exactly its own channel count (chunks of
+// at most MAXCH), so a C=1 image in a mixed batch does not pay for the widest image's channels.
+template <int MAXCH>
+__global__ void __launch_bounds__(kTX* kWarps)
+rw_step_tma_kernel(const __grid_constant__ RwMaps maps, const double* __restrict__ inv_s, double* __restrict__ yout,
+                   const int* __restrict__ chan_off, int h, int w, int pitch) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];   // TMA destinations need 128-byte alignment
+    double* s_y = (double*)smem_raw;                                                 // [<=MAXCH][kYH][kSW]
+    float* s_w = (float*)(smem_raw + (size_t)MAXCH * kYH * kSW * sizeof(double));   // [2][<=9][kWH][kSW]
+    uint64_t* bars = (uint64_t*)(s_w + 2 * kWBufFloats);                            // [0]=y, [1],[2]=weight buffers
+
+    const int tid = threadIdx.x;
+    const int tiles_x = (w + kTX - 1) / kTX;
+    const int x0 = (blockIdx.x % tiles_x) * kTX, y0 = (blockIdx.x / tiles_x) * kTY;
+    const int img = blockIdx.y;
+    const int c_begin = chan_off[img], c_end = chan_off[img + 1];
+    if (c_begin >= c_end) return;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t ph_y = 0, ph_w0 = 0, ph_w1 = 0;
+    int c0 = c_begin;
+    while (c0 < c_end) {
+        const int n = c_end - c0 < MAXCH ? c_end - c0 : MAXCH;
+        if (MAXCH >= 4 && n == 4) rw_chunk<4>(maps, inv_s, yout, s_y, s_w, bars, ph_y, ph_w0, ph_w1, img, c0, c_end, x0, y0, h, w, pitch);
+        else if (MAXCH >= 3 && n == 3) rw_chunk<3>(maps, inv_s, yout, s_y, s_w, bars, ph_y, ph_w0, ph_w1, img, c0, c_end, x0, y0, h, w, pitch);
+        else if (MAXCH >= 2 && n == 2) rw_chunk<2>(maps, inv_s, yout, s_y, s_w, bars, ph_y, ph_w0, ph_w1, img, c0, c_end, x0, y0, h, w, pitch);
+        else rw_chunk<1>(maps, inv_s, yout, s_y, s_w, bars, ph_y, ph_w0, ph_w1, img, c0, c_end, x0, y0, h, w, pitch);
+        c0 += n;
         __syncthreads();   // s_y / weight buffers are reused by the next channel chunk
     }
 }
@@ -428,7 +443,7 @@ rw_step_ring_kernel(const __grid_constant__ RwMaps maps, const double* __restric
                     const uint32_t ys = ny & 1;
                     mbar_wait(&emptyY[ys], ((ny >> 1) & 1) ^ 1);
                     mbar_arrive_expect_tx(&fullY[ys], (uint32_t)Cfg::kYBytes);
-                    tma_load_3d((unsigned char*)s_y + ys * Cfg::kYBytes, &maps.y, &fullY[ys], x0 - kR, y0 - kR, c0);
+                    tma_load_3d((unsigned char*)s_y + ys * Cfg::kYBytes, &maps.y[CH - 1], &fullY[ys], x0 - kR, y0 - kR, c0);
                     ++ny;
 #pragma unroll
                     for (int cls = 0; cls < 5; ++cls) {
@@ -558,9 +573,11 @@ static int launch_tma_steps(const RwWorkspace& ws, int n_img, int totc, int h, i
         }
         const uint64_t dims[3] = {(uint64_t)w, (uint64_t)h, (uint64_t)totc};
         const uint64_t strides[2] = {(uint64_t)pitch * sizeof(double), (uint64_t)pitch * h * sizeof(double)};
-        const uint32_t box[3] = {(uint32_t)kSW, (uint32_t)kYH, (uint32_t)CH};
-        int rc = make_tensor_map(&maps[b].y, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ws.y[b], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
-        if (rc) return rc;
+        for (int d = 1; d <= 4; ++d) {
+            const uint32_t box[3] = {(uint32_t)kSW, (uint32_t)kYH, (uint32_t)d};
+            int rc = make_tensor_map(&maps[b].y[d - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ws.y[b], dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc) return rc;
+        }
     }
     const int tiles_x = (w + kTX - 1) / kTX, tiles_y = (h + kTY - 1) / kTY;
     if (variant != 3) {   // production: three 4-warp CTAs per SM, two weight buffers each (measured faster than the ring below for C >= 2)
