@@ -41,6 +41,7 @@ FLAGS = [
 ]
 PASSES = ["train_cam", "make_cam", "eval_cam", "cam_to_ir_label", "train_irn", "make_ins_seg", "eval_ins_seg", "make_sem_seg", "eval_sem_seg"]
 HOT_STEPS = {"make_cam": "make_cam", "make_ins_seg": "make_ins_seg_labels", "make_sem_seg": "make_sem_seg_labels"}   # pass -> module
+EVAL_STEPS = {"eval_cam": "eval_cam", "eval_sem_seg": "eval_sem_seg"}   # host-side evaluators (need VOC ground truth)
 
 
 def parse(argv=None):
@@ -67,6 +68,10 @@ def main(argv=None):
     import importlib
     for name in PASSES:
         if not getattr(args, name + "_pass"):
+            continue
+        if name in EVAL_STEPS and not args.synthetic and os.path.isdir(os.path.join(args.voc12_root, "SegmentationClass")):
+            pyutils.Timer("step.%s:" % name)
+            importlib.import_module("irn_b200.step." + EVAL_STEPS[name]).run(args)
             continue
         if name not in HOT_STEPS:
             print("[irn_b200] step.%s is outside the B200 hot path: run the reference's own step for it" % name)
