@@ -17,12 +17,14 @@ def main():
     ap.add_argument("--iters", type=int, default=256)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--mix", action="store_true", help="per-image channel counts of bench.py's synthetic batch (1..3 classes)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     h = w = a.hw
     edges = torch.from_numpy(np.concatenate([synth.edge_map(h, w, "bimodal", i) for i in range(a.n_img)], 0)).to(dev)
-    offs = np.arange(a.n_img + 1) * a.c
-    x = torch.rand((a.n_img * a.c, h, w), device=dev)
+    counts = [int(synth.label(i).sum()) for i in range(a.n_img)] if a.mix else [a.c] * a.n_img
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    x = torch.rand((int(offs[-1]), h, w), device=dev)
     for _ in range(2):
         indexing.random_walk_batch(x, edges, offs, n_iter=a.iters, variant=a.variant)
     torch.cuda.synchronize()
@@ -37,8 +39,9 @@ def main():
     ms = float(np.median(ts))
     N = h * w
     e = 8
-    alg = a.n_img * (N * (4 + 4 * a.c + 4 * a.c) + a.iters * N * (4 * 34 + 4 + 2 * e * a.c))
-    print(json.dumps({"n_img": a.n_img, "C": a.c, "hw": a.hw, "iters": a.iters, "variant": a.variant, "ms": ms,
+    totc = int(offs[-1])
+    alg = a.iters * N * (a.n_img * (4 * 34 + 8) + 2 * e * totc)      # step launches only (bench.py's definition)
+    print(json.dumps({"n_img": a.n_img, "C": a.c if not a.mix else "mix(%d)" % totc, "hw": a.hw, "iters": a.iters, "variant": a.variant, "ms": ms,
                       "ms_per_image": ms / a.n_img, "us_per_iter": 1e3 * ms / max(a.iters, 1),
                       "alg_GBps": alg / ms / 1e6, "launches": _lib.lib().irn_rw_last_launch_count()}))
 
