@@ -337,7 +337,7 @@ conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     const int m_tiles = args.tiles_x * args.tiles_y * args.B;
     const int total = m_tiles * n_tiles;
     const int cblocks = args.Cin / kTcBK;
-    const int KB = args.ksize * args.ksize * cblocks;
+    const int KB = args.mode == 1 ? args.ksize : args.ksize * args.ksize * cblocks;   // mode 1 = stem: one k-block per filter row
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -385,7 +385,10 @@ conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                     const int tap = kb / cblocks, cb = kb % cblocks;
                     const int r = tap / args.ksize, ss = tap % args.ksize;
                     mbar_arrive_expect_tx(&full[s], 16384u + 2u * BN * 128u);
-                    tma_load_4d(st, &maps.a, &full[s], cb * kTcBK, ox0 * args.stride - args.pad + ss, oy0 * args.stride - args.pad + r, b);
+                    if (args.mode == 1)
+                        tma_load_4d(st, &maps.a, &full[s], 0, ox0, oy0 * 2 + kb, b);
+                    else
+                        tma_load_4d(st, &maps.a, &full[s], cb * kTcBK, ox0 * args.stride - args.pad + ss, oy0 * args.stride - args.pad + r, b);
                     tma_load_2d(st + 32768, &maps.b_hi, &full[s], kb * kTcBK, n0);
                     tma_load_2d(st + 32768 + BN * 128, &maps.b_lo, &full[s], kb * kTcBK, n0);
                 }

@@ -253,8 +253,12 @@ static int launch_tc(const Conv& c, const float* in, int B, int H, int W, int Ho
 // Tensor-core stem: x4 = zero-haloed NHWC4 input [B, Hin+6, Win+8, 4]; out NHWC [B,Ho,Wo,64] with bias + ReLU.
 static int launch_tc_stem(const Conv& c, const float* x4, int B, int Hin, int Win, float* out, cudaStream_t st) {
     static bool attr_set = false;
+    static int n_sm = 0;
     if (!attr_set) {
-        IRN_CUDA(cudaFuncSetAttribute((conv_tc_kernel<64, 3, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(64, 3)));
+        IRN_CUDA(cudaFuncSetAttribute(conv_tc_persist_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcPersistCfg<64>::kSmem));
+        int dev = 0;
+        IRN_CUDA(cudaGetDevice(&dev));
+        IRN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         attr_set = true;
     }
     const int Hp = Hin + 6, Wp = Win + 8;
@@ -276,9 +280,9 @@ static int launch_tc_stem(const Conv& c, const float* x4, int B, int Hin, int Wi
     a.tiles_x = (Wo + kTcTW - 1) / kTcTW;
     a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
     a.mode = 1;
-    dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B), 1);
-    conv_tc_kernel<64, 3, 3><<<grid, kTcThreads, tc_smem_bytes(64, 3), st>>>(maps, a);
-    IRN_LAUNCH_CHECK("conv_tc_kernel(stem)");
+    const long long total = (long long)a.tiles_x * a.tiles_y * B;
+    conv_tc_persist_kernel<64><<<(unsigned)(total < n_sm ? total : n_sm), kTcPersistThreads, TcPersistCfg<64>::kSmem, st>>>(maps, a);
+    IRN_LAUNCH_CHECK("conv_tc_persist_kernel(stem)");
     return kOk;
 }
 

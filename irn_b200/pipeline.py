@@ -33,6 +33,7 @@ class PseudoLabelPipeline:
         self.cam, self.irn, self.device = cam_model, irn_model, device
         self.scales, self.beta, self.exp_times, self.bg = scales, beta, exp_times, bg_thres
         self.cam_sub, self.rw_sub = cam_sub_batch, rw_sub_batch
+        self._copy_stream = None
         if 1.0 not in scales:
             raise ValueError("the IRNet pass uses the scale-1.0 input (step/make_sem_seg_labels.py:64-66)")
 
@@ -42,11 +43,31 @@ class PseudoLabelPipeline:
         labels: [N,20] multi-hot; size=(H,W).  Returns dict with 'labels' uint8 cuda [N,H,W], 'keys' list,
         'cams' list of cuda [K_i,h4,w4] and 'high_res' list (or None)."""
         dev = self.device
-        xs = [x.to(dev, non_blocking=True) if not x.is_cuda else x for x in inputs]
+        # host inputs: copy on a side stream, one event per scale, so the forward of scale k overlaps the H2D of scale k+1..
+        xs, ready = [], []
+        main = torch.cuda.current_stream(dev)
+        if any(not x.is_cuda for x in inputs):
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copy_stream.wait_stream(main)          # buffers freed on the main stream may be recycled for the copies
+        for x in inputs:
+            if x.is_cuda:
+                xs.append(x)
+                ready.append(None)
+            else:
+                with torch.cuda.stream(self._copy_stream):
+                    xd = x.to(dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                xd.record_stream(main)
+                xs.append(xd)
+                ready.append(ev)
         N = xs[0].shape[0] // 2
         # ---- C2/C3: CAM forward per scale, in sub-batches of image pairs
         cams = []
-        for x, s in zip(xs, self.scales):
+        for x, s, ev in zip(xs, self.scales, ready):
+            if ev is not None:
+                main.wait_event(ev)
             # sub-batch so that every forward sees about the same number of pixels (cam_sub images at scale 2.0):
             # small scales batch more images to keep all SMs busy, large scales bound the activation arena
             sub = max(1, int(self.cam_sub * (2.0 / s) ** 2))

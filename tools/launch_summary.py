@@ -23,8 +23,9 @@ def load(path):
 
 def key(n):
     k = re.sub(r"<.*", "", n.split("(")[0]).replace("void ", "").replace("irn::", "")
-    if "conv_tc" in n:
-        k = "conv_tc_kernel" + ("<64>" if "<64>" in n else "<128>")
+    m = re.search(r"(conv_tc\w*kernel)(<[^>]*>)?", n)
+    if m:
+        k = m.group(1) + (m.group(2) or "")
     return k
 
 
