@@ -34,6 +34,7 @@ class PseudoLabelPipeline:
         self.scales, self.beta, self.exp_times, self.bg = scales, beta, exp_times, bg_thres
         self.cam_sub, self.rw_sub = cam_sub_batch, rw_sub_batch
         self._copy_stream = None
+        self._staging = {}
         if 1.0 not in scales:
             raise ValueError("the IRNet pass uses the scale-1.0 input (step/make_sem_seg_labels.py:64-66)")
 
@@ -44,35 +45,42 @@ class PseudoLabelPipeline:
         'cams' list of cuda [K_i,h4,w4] and 'high_res' list (or None)."""
         dev = self.device
         # host inputs: copy on a side stream, one event per scale, so the forward of scale k overlaps the H2D of scale k+1..
-        xs, ready = [], []
         main = torch.cuda.current_stream(dev)
         if any(not x.is_cuda for x in inputs):
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=dev)
             self._copy_stream.wait_stream(main)          # buffers freed on the main stream may be recycled for the copies
-        for x in inputs:
+        order = sorted(range(len(inputs)), key=lambda k: inputs[k].numel())     # smallest scale first: least exposed copy
+        xs, ready = [None] * len(inputs), [None] * len(inputs)
+        for k in order:
+            x = inputs[k]
             if x.is_cuda:
-                xs.append(x)
-                ready.append(None)
+                xs[k] = x
             else:
+                # persistent device staging buffers (no allocator traffic across streams); the wait_stream above guarantees the
+                # previous step has finished reading them
+                buf = self._staging.get(k)
+                if buf is None or buf.shape != x.shape:
+                    buf = torch.empty(x.shape, dtype=torch.float32, device=dev)
+                    self._staging[k] = buf
                 with torch.cuda.stream(self._copy_stream):
-                    xd = x.to(dev, non_blocking=True)
+                    buf.copy_(x, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(self._copy_stream)
-                xd.record_stream(main)
-                xs.append(xd)
-                ready.append(ev)
+                xs[k] = buf
+                ready[k] = ev
         N = xs[0].shape[0] // 2
         # ---- C2/C3: CAM forward per scale, in sub-batches of image pairs
-        cams = []
-        for x, s, ev in zip(xs, self.scales, ready):
-            if ev is not None:
-                main.wait_event(ev)
+        cams = [None] * len(xs)
+        for k in order:                                   # compute in copy order; `cams` stays in self.scales order for the merge
+            x, s = xs[k], self.scales[k]
+            if ready[k] is not None:
+                main.wait_event(ready[k])
             # sub-batch so that every forward sees about the same number of pixels (cam_sub images at scale 2.0):
             # small scales batch more images to keep all SMs busy, large scales bound the activation arena
             sub = max(1, int(self.cam_sub * (2.0 / s) ** 2))
             outs = [self.cam.forward_batch(x[2 * i:2 * min(i + sub, N)]) for i in range(0, N, sub)]
-            cams.append(torch.cat(outs, 0))
+            cams[k] = torch.cat(outs, 0)
         # ---- C4: merge + normalise per image (classes present differ per image)
         keys, strided, highres = [], [], []
         for i in range(N):
