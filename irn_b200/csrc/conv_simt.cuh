@@ -254,6 +254,20 @@ __global__ void cam_head_kernel(const float* __restrict__ feat, const float* __r
     }
 }
 
+// CAM head tail for the tensor-core path: y = relu(classifier(x)) is already in t NHWC [2P,h,w,C] (first 20 channels real);
+// out[p,n,y,x] = t[2p,y,x,n] + t[2p+1,y,w-1-x,n]      (net/resnet50_cam.py:68)
+__global__ void cam_flip_add_kernel(const float* __restrict__ t, float* __restrict__ out, int P, int h, int w, int C) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)P * 20 * h * w) return;
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const int n = (int)((i / ((size_t)w * h)) % 20);
+    const int p = (int)(i / ((size_t)w * h * 20));
+    const float a = t[(((size_t)(2 * p) * h + y) * w + x) * C + n];
+    const float b = t[(((size_t)(2 * p + 1) * h + y) * w + (w - 1 - x)) * C + n];
+    out[i] = a + b;
+}
+
 // GroupNorm statistics, pass 1: per (sample, group) sum and sum of squares in fp64.  grid (slices, B), 256 threads;
 // thread t owns channel t % C of every (256/C)-th pixel of its slice, so global reads are fully coalesced; the
 // per-channel partials are folded per group through shared-memory atomics, then one atomicAdd per group per block.

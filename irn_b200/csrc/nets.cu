@@ -51,7 +51,8 @@ struct irn_net {
     irn::Conv stem;
     std::vector<irn::Block> blocks[4];
     // CAM
-    float* classifier = nullptr;   // [20][2048]
+    float* classifier = nullptr;   // [20][2048] (SIMT head kernel)
+    irn::Conv cls_conv;            // the same weights as a 2048 -> 64 1x1 conv (rows 20..63 zero) for the tensor-core path
     // IRN
     irn::Head edge[5], dp[7];
     float* edge6_w = nullptr;      // [1][160]
@@ -574,7 +575,16 @@ extern "C" int irn_cam_net_create(const float* params, size_t n_floats, irn_net*
     net->kind = 0;
     Reader rd{params, n_floats};
     int rc = read_trunk(net, rd);
-    if (!rc) rc = read_vec(net, rd, (size_t)20 * 2048, &net->classifier);
+    if (!rc) {
+        const float* cw = rd.p;
+        rc = read_vec(net, rd, (size_t)20 * 2048, &net->classifier);
+        if (!rc) {
+            std::vector<float> padded((size_t)64 * 2048, 0.f);
+            std::memcpy(padded.data(), cw, (size_t)20 * 2048 * sizeof(float));
+            Reader r2{padded.data(), padded.size()};
+            rc = read_conv(net, r2, net->cls_conv, 2048, 64, 1, 1, 0, false);
+        }
+    }
     if (!rc && rd.left != 0) rc = fail(kBadArg, "irn_cam_net_create: %zu unread floats in the parameter blob", rd.left);
     if (rc) {
         irn_net_destroy(net);
@@ -611,7 +621,8 @@ extern "C" int irn_irn_net_create(const float* params, size_t n_floats, irn_net*
 
 extern "C" size_t irn_cam_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || (B & 1) || H <= 0 || W <= 0) return 0;
-    return (trunk_workspace_floats(B, H, W, false) + 64) * sizeof(float);
+    const TrunkShapes sh = trunk_shapes(B, H, W);
+    return (trunk_workspace_floats(B, H, W, false) + (size_t)B * sh.Hl[3] * sh.Wl[3] * 64 + 128) * sizeof(float);
 }
 
 // CAM.forward for P = B/2 (image, flipped image) pairs: x NCHW fp32 [B,3,H,W] -> cam [P,20,ceil(H/16),ceil(W/16)]
@@ -628,6 +639,17 @@ extern "C" int irn_cam_forward(const irn_net* net, const float* x_nchw, int B, i
     int rc = run_trunk(net, x_nchw, B, H, W, H, W, ar, false, feats, sh, st);
     if (rc) return rc;
     const int P = B / 2, h = sh.Hl[3], w = sh.Wl[3];
+    if (net->conv_mode == 1 && net->cls_conv.bn) {
+        // classifier as a 2048 -> 64 tensor-core conv with fused ReLU (the one-warp-per-pixel head re-reads the 160 KB weight
+        // matrix per pixel), then flip-add + NHWC -> NCHW on the 20 real channels
+        float* tmp = ar.take((size_t)B * h * w * 64);
+        if (!ar.ok) return fail(kWorkspace, "irn_cam_forward: workspace too small");
+        if ((rc = run_conv(net, net->cls_conv, feats[4], B, h, w, nullptr, tmp, true, st, nullptr, nullptr))) return rc;
+        const size_t total = (size_t)P * 20 * h * w;
+        cam_flip_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tmp, cam_out, P, h, w, 64);
+        IRN_LAUNCH_CHECK("cam_flip_add_kernel");
+        return kOk;
+    }
     const size_t warps = (size_t)P * h * w;
     cam_head_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(feats[4], net->classifier, cam_out, P, h, w, 2048);
     IRN_LAUNCH_CHECK("cam_head_kernel");
