@@ -101,13 +101,13 @@ int irn_rw_last_step_ms(float* ms_per_step, int* n_steps);
  * divide by the global max, prepend a constant background plane, argmax (ties -> lowest
  * index), map through keys.
  *
- *  rw   fp32 [C,h,w] one image;  keys_dev device int32 [C+1] (entry 0 = background id) or
- *  NULL (identity);  outputs, each optional (NULL): labels uint8 [H,W] = keys[argmax];
+ *  rw   fp32 [C,h,w] one image;  keys_host HOST int32 [C+1] (entry 0 = background id, C+1 <= 64;
+ *  passed to the kernel by value: no copy, no synchronisation) or NULL (identity);  outputs, each optional (NULL): labels uint8 [H,W] = keys[argmax];
  *  index_out int32 [H,W] = raw argmax (instance path: C may exceed 255);  up_norm fp32
  *  [C,H,W] = normalised upsampled scores (instance scoring).  scratch: device, >= 16 bytes.
  */
 int irn_rw_labels(const float* rw, int C, int h, int w, int H, int W, float bg_thres,
-                  const int32_t* keys_dev, uint8_t* labels, int32_t* index_out, float* up_norm,
+                  const int32_t* keys_host, uint8_t* labels, int32_t* index_out, float* up_norm,
                   void* scratch, irn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
@@ -163,12 +163,12 @@ int irn_edge_displacement_forward(const irn_net* net, const float* x_nchw, int P
 /* ------------------------------------------------------------------------------------
  * C4  multi-scale CAM merge.  Replaces step/make_cam.py:38-52.
  *   cams: HOST array of n_scales DEVICE pointers, each fp32 [20,hs[s],ws[s]] (CAM.forward outputs);
- *   (H,W) original image size; keys_dev device int32 [K] = classes present (torch.nonzero(label));
+ *   (H,W) original image size; keys_host HOST int32 [K] = classes present (torch.nonzero(label)), by value;
  *   strided_out fp32 [K,ceil(H/4),ceil(W/4)], highres_out fp32 [K,H,W] (either may be NULL):
  *   sum over scales of the bilinear (align_corners=False) resample, each kept class / (max + 1e-5).
  *   scratch: device, >= 2*K*4 bytes. */
 int irn_cam_merge(const float* const* cams, const int* hs, const int* ws, int n_scales, int H, int W,
-                  const int32_t* keys_dev, int K, float* strided_out, float* highres_out,
+                  const int32_t* keys_host, int K, float* strided_out, float* highres_out,
                   void* scratch, irn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------

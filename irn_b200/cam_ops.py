@@ -26,10 +26,10 @@ def merge_cams(outputs, size, label):
     ptrs = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
     hs = (ctypes.c_int * n)(*[int(o.shape[1]) for o in outs])
     ws = (ctypes.c_int * n)(*[int(o.shape[2]) for o in outs])
-    keys_dev = keys.to(torch.int32).to(dev)
+    keys_host = np.ascontiguousarray(keys.numpy().astype(np.int32))
     scratch = torch.empty(2 * K + 4, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        rc = L.irn_cam_merge(ptrs, hs, ws, n, H, W, _lib.ptr(keys_dev), K, _lib.ptr(strided), _lib.ptr(highres), _lib.ptr(scratch),
+        rc = L.irn_cam_merge(ptrs, hs, ws, n, H, W, keys_host.ctypes.data, K, _lib.ptr(strided), _lib.ptr(highres), _lib.ptr(scratch),
                              _lib.stream_ptr())
     _lib.check(rc, "irn_cam_merge")
     return keys, strided, highres

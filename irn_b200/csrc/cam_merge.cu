@@ -12,6 +12,7 @@ struct MergeArgs {
     const float* cam[kMaxScales];   // each [20, hs, ws]
     int hs[kMaxScales], ws[kMaxScales];
     int n_scales, n_cls;
+    int keys[20];                   // classes present (<= 20), by value
 };
 
 __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
@@ -25,14 +26,14 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
 }
 
 // out[k, y, x] (y < Hc, x < Wc) = sum over scales of the bilinear resample to a (Ho, Wo) grid; also tracks max per k
-__global__ void cam_merge_kernel(MergeArgs a, const int* __restrict__ keys, int K, int Ho, int Wo, int Hc, int Wc,
+__global__ void cam_merge_kernel(MergeArgs a, int K, int Ho, int Wo, int Hc, int Wc,
                                  float* __restrict__ out, int* __restrict__ max_bits) {
     const int k = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float v = 0.f;
     if (i < Hc * Wc) {
         const int y = i / Wc, x = i % Wc;
-        const int cls = keys[k];
+        const int cls = a.keys[k];
         for (int s = 0; s < a.n_scales; ++s) {
             const int hs = a.hs[s], ws = a.ws[s];
             int y0, y1, x0, x1;
@@ -63,17 +64,22 @@ __global__ void cam_norm_kernel(float* __restrict__ x, const int* __restrict__ m
 
 using namespace irn;
 
-extern "C" int irn_cam_merge(const float* const* cams, const int* hs, const int* ws, int n_scales, int H, int W, const int32_t* keys_dev,
+extern "C" int irn_cam_merge(const float* const* cams, const int* hs, const int* ws, int n_scales, int H, int W, const int32_t* keys_host,
                              int K, float* strided_out, float* highres_out, void* scratch, irn_stream_t stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     launch_counter() = 0;
     if (!cams || !hs || !ws || !scratch || n_scales <= 0 || n_scales > kMaxScales || H <= 0 || W <= 0 || K < 0)
         return fail(kBadArg, "irn_cam_merge: bad argument (n_scales must be 1..%d)", kMaxScales);
     if (K == 0) return kOk;
-    if (!keys_dev || (!strided_out && !highres_out)) return fail(kBadArg, "irn_cam_merge: null pointer");
+    if (!keys_host || (!strided_out && !highres_out)) return fail(kBadArg, "irn_cam_merge: null pointer");
+    if (K > 20) return fail(kBadArg, "irn_cam_merge: K=%d exceeds the 20 VOC classes", K);
     MergeArgs a;
     a.n_scales = n_scales;
     a.n_cls = 20;
+    for (int k = 0; k < K; ++k) {
+        if (keys_host[k] < 0 || keys_host[k] >= 20) return fail(kBadArg, "irn_cam_merge: class id %d out of range", keys_host[k]);
+        a.keys[k] = keys_host[k];
+    }
     for (int s = 0; s < n_scales; ++s) {
         a.cam[s] = cams[s];
         a.hs[s] = hs[s];
@@ -85,14 +91,14 @@ extern "C" int irn_cam_merge(const float* const* cams, const int* hs, const int*
     const int Hu = ((H - 1) / 16 + 1) * 16, Wu = ((W - 1) / 16 + 1) * 16;   // misc/imutils.py:177-179
     if (strided_out) {
         dim3 grid((h4 * w4 + 255) / 256, K);
-        cam_merge_kernel<<<grid, 256, 0, st>>>(a, keys_dev, K, h4, w4, h4, w4, strided_out, mx);
+        cam_merge_kernel<<<grid, 256, 0, st>>>(a, K, h4, w4, h4, w4, strided_out, mx);
         IRN_LAUNCH_CHECK("cam_merge_kernel(strided)");
         cam_norm_kernel<<<grid, 256, 0, st>>>(strided_out, mx, h4 * w4);
         IRN_LAUNCH_CHECK("cam_norm_kernel(strided)");
     }
     if (highres_out) {
         dim3 grid((H * W + 255) / 256, K);
-        cam_merge_kernel<<<grid, 256, 0, st>>>(a, keys_dev, K, Hu, Wu, H, W, highres_out, mx + K);
+        cam_merge_kernel<<<grid, 256, 0, st>>>(a, K, Hu, Wu, H, W, highres_out, mx + K);
         IRN_LAUNCH_CHECK("cam_merge_kernel(highres)");
         cam_norm_kernel<<<grid, 256, 0, st>>>(highres_out, mx + K, H * W);
         IRN_LAUNCH_CHECK("cam_norm_kernel(highres)");

@@ -6,6 +6,11 @@
 
 namespace irn {
 
+struct LabelKeys {     // class id per argmax index (entry 0 = background), passed by value: no device copy, no host sync
+    int n;
+    int v[64];
+};
+
 // torch upsample_bilinear2d, align_corners=False, scale_factor=4: src = max(0,(dst+0.5)/4-0.5)
 __device__ __forceinline__ void src_index4(int dst, int in_size, int& i0, int& i1, float& l1) {
     float s = ((float)dst + 0.5f) * 0.25f - 0.5f;
@@ -48,7 +53,7 @@ __global__ void labels_max_kernel(const float* __restrict__ rw, int C, int h, in
 
 // pass 2: normalise, argmax against the background plane, map through keys
 __global__ void labels_argmax_kernel(const float* __restrict__ rw, int C, int h, int w, int H, int W, float bg,
-                                     const int* __restrict__ keys, const int* __restrict__ gmax_bits,
+                                     LabelKeys keys, const int* __restrict__ gmax_bits,
                                      uint8_t* __restrict__ labels, int32_t* __restrict__ index_out,
                                      float* __restrict__ up_norm) {
     const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y;
@@ -68,7 +73,7 @@ __global__ void labels_argmax_kernel(const float* __restrict__ rw, int C, int h,
             arg = c + 1;
         }
     }
-    if (labels) labels[(size_t)Y * W + X] = (uint8_t)(keys ? keys[arg] : arg);
+    if (labels) labels[(size_t)Y * W + X] = (uint8_t)(keys.n ? keys.v[arg] : arg);
     if (index_out) index_out[(size_t)Y * W + X] = arg;
 }
 
@@ -76,18 +81,25 @@ __global__ void labels_argmax_kernel(const float* __restrict__ rw, int C, int h,
 
 using namespace irn;
 
-extern "C" int irn_rw_labels(const float* rw, int C, int h, int w, int H, int W, float bg_thres, const int32_t* keys_dev,
+extern "C" int irn_rw_labels(const float* rw, int C, int h, int w, int H, int W, float bg_thres, const int32_t* keys_host,
                              uint8_t* labels, int32_t* index_out, float* up_norm, void* scratch, irn_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     launch_counter() = 0;
     if (!rw || !scratch || (!labels && !index_out && !up_norm)) return fail(kBadArg, "irn_rw_labels: null pointer");
     if (C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || H > 4 * h || W > 4 * w)
         return fail(kBadArg, "irn_rw_labels: bad sizes C=%d h=%d w=%d H=%d W=%d (need H<=4h, W<=4w)", C, h, w, H, W);
+    LabelKeys keys;
+    keys.n = 0;
+    if (keys_host) {
+        if (C + 1 > 64) return fail(kUnsupported, "irn_rw_labels: a key table of %d entries exceeds 64 (pass NULL and map the index map on the host)", C + 1);
+        keys.n = C + 1;
+        for (int i = 0; i <= C; ++i) keys.v[i] = keys_host[i];
+    }
     IRN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int), stream));
     dim3 block(128), grid((W + 127) / 128, H);
     labels_max_kernel<<<grid, block, 0, stream>>>(rw, C, h, w, H, W, (int*)scratch);
     IRN_LAUNCH_CHECK("labels_max_kernel");
-    labels_argmax_kernel<<<grid, block, 0, stream>>>(rw, C, h, w, H, W, bg_thres, keys_dev, (const int*)scratch, labels,
+    labels_argmax_kernel<<<grid, block, 0, stream>>>(rw, C, h, w, H, W, bg_thres, keys, (const int*)scratch, labels,
                                                      index_out, up_norm);
     IRN_LAUNCH_CHECK("labels_argmax_kernel");
     return kOk;

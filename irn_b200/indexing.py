@@ -62,6 +62,16 @@ def _workspace(nbytes, device):
     return ws
 
 
+_scratches = {}
+
+
+def _scratch(device):
+    key = (device.type, device.index)
+    if key not in _scratches:
+        _scratches[key] = torch.empty(256, dtype=torch.uint8, device=device)
+    return _scratches[key]
+
+
 def edge_to_affinity(edge, radius=5):
     """misc/indexing.py:91-109 on the un-padded grid.  edge cuda fp32 [B,h,w] (or [h,w]) ->
     [B, n_dst, h, w]; channel order = PathIndex.search_dst order."""
@@ -125,13 +135,12 @@ def rw_labels(rw, keys, size, bg_thres=0.25, want_index=False, want_scores=False
     labels = torch.empty((H, W), dtype=torch.uint8, device=dev)
     index = torch.empty((H, W), dtype=torch.int32, device=dev) if want_index else None
     scores = torch.empty((C, H, W), dtype=torch.float32, device=dev) if want_scores else None
-    kd = None
+    kh = None
     if keys is not None:
-        k = np.pad(np.asarray(keys, dtype=np.int64) + 1, (1, 0), mode="constant").astype(np.int32)
-        kd = torch.from_numpy(k).to(dev)
-    scratch = torch.empty(16, dtype=torch.uint8, device=dev)
+        kh = np.ascontiguousarray(np.pad(np.asarray(keys, dtype=np.int64) + 1, (1, 0), mode="constant").astype(np.int32))
+    scratch = _scratch(dev)
     with torch.cuda.device(dev):
-        rc = L.irn_rw_labels(_lib.ptr(r), C, h, w, H, W, float(bg_thres), _lib.ptr(kd), _lib.ptr(labels), _lib.ptr(index),
+        rc = L.irn_rw_labels(_lib.ptr(r), C, h, w, H, W, float(bg_thres), kh.ctypes.data if kh is not None else None, _lib.ptr(labels), _lib.ptr(index),
                              _lib.ptr(scores), _lib.ptr(scratch), _lib.stream_ptr())
     _lib.check(rc, "irn_rw_labels")
     return labels, index, scores
