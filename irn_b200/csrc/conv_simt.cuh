@@ -306,14 +306,16 @@ gn_partial_kernel(const float* __restrict__ x, double* __restrict__ sums, int HW
 
 // GroupNorm affine -> bilinear upsample by `up` (align_corners=False) -> ReLU, written into a channel slice
 // of a concat buffer, cropped to (Hd, Wd)   (net/resnet50_irn.py:23-93,117-131: conv -> GN -> Upsample -> ReLU).
+// One thread = 4 consecutive channels (same group: groups hold >= 8 channels); coff and Cd are multiples of 4.
 __global__ void gn_up_relu_kernel(const float* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, float* __restrict__ dst, int B, int H, int W, int C, int G, int up,
                                   int Hd, int Wd, int Cd, int coff) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)B * Hd * Wd * C;
+    const int C4 = C >> 2;
+    const size_t total = (size_t)B * Hd * Wd * C4;
     if (i >= total) return;
-    const int c = (int)(i % C);
-    size_t r = i / C;
+    const int c = (int)(i % C4) * 4;
+    size_t r = i / C4;
     const int X = (int)(r % Wd);
     r /= Wd;
     const int Y = (int)(r % Hd);
@@ -325,11 +327,20 @@ __global__ void gn_up_relu_kernel(const float* __restrict__ x, const double* __r
     double var = sums[2 * (b * G + g) + 1] / cnt - mu * mu;
     var = var < 0.0 ? 0.0 : var;
     const float mean = (float)mu, rstd = (float)(1.0 / sqrt(var + 1e-5));
-    const float ga = gamma[c], be = beta[c];
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
     const float* xb = x + (size_t)b * H * W * C + c;
-    float v;
+    auto norm = [&](const float4 v) {
+        float4 o;
+        o.x = (v.x - mean) * rstd * ga.x + be.x;
+        o.y = (v.y - mean) * rstd * ga.y + be.y;
+        o.z = (v.z - mean) * rstd * ga.z + be.z;
+        o.w = (v.w - mean) * rstd * ga.w + be.w;
+        return o;
+    };
+    auto ld = [&](int yy, int xx) { return norm(__ldg(reinterpret_cast<const float4*>(xb + ((size_t)yy * W + xx) * C))); };
+    float4 v;
     if (up == 1) {
-        v = (xb[((size_t)Y * W + X) * C] - mean) * rstd * ga + be;
+        v = ld(Y, X);
     } else {
         const float inv = 1.0f / (float)up;
         float sy = ((float)Y + 0.5f) * inv - 0.5f, sx = ((float)X + 0.5f) * inv - 0.5f;
@@ -340,13 +351,14 @@ __global__ void gn_up_relu_kernel(const float* __restrict__ x, const double* __r
         x0 = x0 > W - 1 ? W - 1 : x0;
         const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
         const float ly = sy - (float)y0, lx = sx - (float)x0;
-        const float v00 = (xb[((size_t)y0 * W + x0) * C] - mean) * rstd * ga + be;
-        const float v01 = (xb[((size_t)y0 * W + x1) * C] - mean) * rstd * ga + be;
-        const float v10 = (xb[((size_t)y1 * W + x0) * C] - mean) * rstd * ga + be;
-        const float v11 = (xb[((size_t)y1 * W + x1) * C] - mean) * rstd * ga + be;
-        v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+        const float4 v00 = ld(y0, x0), v01 = ld(y0, x1), v10 = ld(y1, x0), v11 = ld(y1, x1);
+        v.x = (1.f - ly) * ((1.f - lx) * v00.x + lx * v01.x) + ly * ((1.f - lx) * v10.x + lx * v11.x);
+        v.y = (1.f - ly) * ((1.f - lx) * v00.y + lx * v01.y) + ly * ((1.f - lx) * v10.y + lx * v11.y);
+        v.z = (1.f - ly) * ((1.f - lx) * v00.z + lx * v01.z) + ly * ((1.f - lx) * v10.z + lx * v11.z);
+        v.w = (1.f - ly) * ((1.f - lx) * v00.w + lx * v01.w) + ly * ((1.f - lx) * v10.w + lx * v11.w);
     }
-    dst[(((size_t)b * Hd + Y) * Wd + X) * Cd + coff + c] = fmaxf(v, 0.f);
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    *reinterpret_cast<float4*>(dst + (((size_t)b * Hd + Y) * Wd + X) * Cd + coff + c) = v;
 }
 
 // EdgeDisplacement tail (net/resnet50_irn.py:228-234) for pair p = blockIdx.y: crop to (fh,fw);

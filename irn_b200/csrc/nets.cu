@@ -688,7 +688,7 @@ static int run_head(const irn_net* net, const Head& hd, const float* x, int B, i
         gn_partial_kernel<<<dim3(slices, B), 256, 0, st>>>(raw, (double*)stats, H * W, hd.conv.cout, hd.groups);
         IRN_LAUNCH_CHECK("gn_partial_kernel");
     }
-    const size_t total = (size_t)B * Hd * Wd * hd.conv.cout;
+    const size_t total = (size_t)B * Hd * Wd * (hd.conv.cout / 4);
     gn_up_relu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(raw, (const double*)stats, hd.gamma, hd.beta, dst, B, H, W, hd.conv.cout, hd.groups,
                                                                       hd.up, Hd, Wd, Cd, coff);
     IRN_LAUNCH_CHECK("gn_up_relu_kernel");
