@@ -164,6 +164,13 @@ def run_reference(a, rank):
                       "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
+def clocks_mhz(clocks):
+    try:
+        return float(clocks.get("sm_mhz") or 1800.0)
+    except Exception:
+        return 1800.0
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -199,7 +206,7 @@ def main():
     cam.cuda(dev), irn.cuda(dev)
     for m in (cam, irn):
         _lib.check(L.irn_net_set_conv_mode(m._get_plan(dev).handle, a.conv_mode))
-    pipe = PseudoLabelPipeline(cam, irn, dev, SCALES, rw_sub_batch=32)
+    pipe = PseudoLabelPipeline(cam, irn, dev, SCALES, rw_sub_batch=64)
 
     # ---- synthetic inputs: rank r takes images r, r+N, ... of the global list (misc/torchutils.py:66-68)
     B = a.batch
@@ -275,17 +282,40 @@ def main():
         counts = [len(k) for k in out["keys"]]
         last = counts[-(len(counts) % pipe.rw_sub or pipe.rw_sub):]
         n_img, totc, N = len(last), sum(last), (H // 4) * (W // 4)
-        alg = N * (n_img * (4 * 34 + 8) + 2 * 8 * totc)      # per launch: fp32 weights + fp64 1/s + fp64 state read+write
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "rw_step_traffic.json")))["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        ach = alg / (step_ms.value * 1e-3) / 1e9
-        roofline = {"kernel": "rw_step_tma_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                    "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                    "launch_us": 1e3 * step_ms.value, "images_per_launch": n_img, "channels_per_launch": totc,
-                    "algorithmic_bytes_per_launch": alg}
+        alg_step = N * (n_img * (4 * 34 + 8) + 2 * 8 * totc)      # per walk step: fp32 weights + fp64 1/s + fp64 state read+write
+        src = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"
+        if L.irn_rw_last_was_fused():
+            # the whole walk is ONE launch: algorithmic bytes = n_iter x the per-step figure (SURVEY.md 8(d) B_rw)
+            launch_ms = step_ms.value * n_it.value
+            alg = alg_step * n_it.value
+            traffic = None
+            try:
+                t = json.load(open(os.path.join(ROOT, "profiles", "rw_fused_traffic.json")))
+                traffic = int(t["dram_bytes_per_item"] * totc)
+            except Exception:
+                pass
+            ach = alg / (launch_ms * 1e-3) / 1e9
+            # the bound the resident design actually runs into: shared-memory wavefronts
+            wf_per_warp_step = (34 * 2 - 16) * 4 + 108 * 2      # weight LDS.32 (16 planes' forward taps come from registers) + state LDS.64 x 2 wavefronts
+            clusters = max(1, int(L.irn_rw_last_was_fused()))
+            per = -(-totc // clusters)                         # items walked by the busiest cluster
+            smem_cycles = wf_per_warp_step * 8 * per * n_it.value   # 8 warps per CTA, one 128-byte wavefront per cycle per SM
+            roofline = {"kernel": "rw_fused_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                        "traffic": traffic, "peak_source": src, "launch_us": 1e3 * launch_ms, "steps_per_launch": n_it.value,
+                        "images_per_launch": n_img, "channels_per_launch": totc, "algorithmic_bytes_per_launch": alg,
+                        "note": "weights stay resident in shared memory for all steps of a launch, so DRAM traffic (`traffic`) is a small "
+                                "fraction of the algorithmic bytes and frac may exceed 1; the kernel's real ceiling is shared-memory bandwidth",
+                        "clusters": clusters, "smem_wavefront_frac": smem_cycles / (launch_ms * 1e-3 * clocks_mhz(clocks) * 1e6)}
+        else:
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "rw_step_traffic.json")))["dram_bytes_per_launch"]
+            except Exception:
+                pass
+            ach = alg_step / (step_ms.value * 1e-3) / 1e9
+            roofline = {"kernel": "rw_step_tma_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                        "traffic": traffic, "peak_source": src, "launch_us": 1e3 * step_ms.value, "images_per_launch": n_img,
+                        "channels_per_launch": totc, "algorithmic_bytes_per_launch": alg_step}
     tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
     ach_tf = world * B * a.steps * GFLOP_PER_IMAGE / (ms_dev / 1e3) / 1e3 / world
     roofline_conv = {"bound": "tensor", "achieved": ach_tf, "unit": "TFLOP/s", "peak": tf32_peak, "frac": ach_tf / tf32_peak,

@@ -76,9 +76,11 @@ int irn_random_walk(const float* x, const float* edge, float* out, int n_img,
                     const int32_t* chan_offsets, int h, int w, int radius, double beta,
                     int n_iter, void* workspace, size_t workspace_bytes, irn_stream_t stream);
 
-/* Same, selecting the step kernel: variant 0 = production (TMA-staged register-window kernel,
- * radius 5), 1 = generic bounds-checked kernel (any radius 2..10; validation / fallback for
- * radii the reference's hot path never uses), 3 = persistent TMA-ring experiment (radius 5). */
+/* Same, selecting the kernel: variant 0 = production (radius 5: the fused cluster kernel -- all
+ * n_iter steps in one launch, weights resident in shared memory -- when h, w <= 128, else the
+ * per-step TMA kernel), 1 = generic bounds-checked step kernel (any radius 2..10; validation /
+ * radii the reference's hot path never uses), 2 = per-step TMA kernel (radius 5), 3 = persistent
+ * TMA-ring step kernel (experiment), 4 = fused cluster kernel, or -4 when it cannot run. */
 int irn_random_walk_variant(const float* x, const float* edge, float* out, int n_img,
                             const int32_t* chan_offsets, int h, int w, int radius, double beta,
                             int n_iter, void* workspace, size_t workspace_bytes, int variant,
@@ -88,6 +90,8 @@ int irn_random_walk_variant(const float* x, const float* edge, float* out, int n
  * (bench.py's gpu_launches). */
 int irn_rw_last_launch_count(void);
 long long irn_total_launch_count(void);
+/* Number of thread-block clusters the last walk on this thread ran on as the fused kernel; 0 when it ran step by step. */
+int irn_rw_last_was_fused(void);
 
 /* Device timing of the walk's step kernels for bench.py's roofline: when enabled, CUDA events are recorded on the
  * caller's stream around the n_iter step launches; irn_rw_last_step_ms waits for the last timed walk and returns

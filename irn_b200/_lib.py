@@ -27,6 +27,7 @@ SIGNATURES = {
     "irn_random_walk_variant": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_double,
                                         c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "irn_rw_last_launch_count": (c_int, []),
+    "irn_rw_last_was_fused": (c_int, []),
     "irn_total_launch_count": (ctypes.c_longlong, []),
     "irn_rw_set_timing": (c_int, [c_int]),
     "irn_rw_last_step_ms": (c_int, [ctypes.POINTER(c_float), _p_int]),

@@ -529,6 +529,216 @@ rw_step_ring_kernel(const __grid_constant__ RwMaps maps, const double* __restric
     }
 }
 
+// ---------------------------------------------------------------- fused walk (radius 5, h,w <= 128): the production path
+// All n_iter steps of one (image, channel) in ONE launch, one thread-block cluster per item:
+//   * the cluster's CTAs own 8 consecutive rows each (cluster size = smallest of 1,2,4,8,16 covering h); every CTA keeps the
+//     34 weight planes of its rows -- plus, for plane (dy,dx), the dy rows above that its mirrored taps read -- resident in
+//     shared memory for the whole walk: (34*8 + 68) rows x 128 fp32 = 170 KB, loaded from HBM ONCE per item instead of
+//     once per step (the step kernel above re-reads 2.2 MB of weights per image per step);
+//   * the fp64 state lives in a double-buffered 16 x 136 shared tile (8 own rows + 4 halo rows either side, 4 zero columns
+//     either side); each step writes the new rows locally and pushes the boundary rows into the neighbour CTAs' halo rows
+//     through distributed shared memory, then ONE cluster barrier publishes them;
+//   * HBM traffic per item = weights + 1/s + seeds in, fp32 result out; nothing per step.
+// The tap order per pixel is the step kernel's, so both produce bit-identical results.
+constexpr int kFR = 8;                       // rows per CTA
+constexpr int kFW = 128;                     // widest supported grid = weight row pitch in shared memory
+constexpr int kFYP = kFW + 2 * kR;           // 136: state row pitch
+constexpr int kFYR = kFR + 2 * kR;           // 16 state rows
+#ifndef IRN_RW_REGPLANES4
+#define IRN_RW_REGPLANES4 16
+#endif
+#ifndef IRN_RW_REGPLANES2
+#define IRN_RW_REGPLANES2 16
+#endif
+constexpr int fused_threads(int py) { return (kFW / 32) * (kFR / py) * 32; }   // py = rows per thread: 4 -> 256, 2 -> 512 threads
+
+__host__ __device__ constexpr int plane_dy5(int k) {   // dy of internal plane k (inverse of plane5)
+    if (k < 4) return k + 1;
+    for (int c = 1; c <= 4; ++c) {
+        const int base = cls_base5(c), m = cls_maxdy5(c);
+        if (k < base + m + 1) return k - base;           // dx = +c, dy = 0..m
+        if (k < base + 2 * m + 1) return k - base - m;   // dx = -c, dy = 1..m
+    }
+    return 0;
+}
+__host__ __device__ constexpr int wrow_base5(int k) {   // first shared-memory row of plane k: it stores rows r0-dy .. r0+7
+    int s = 0;
+    for (int i = 0; i < k; ++i) s += kFR + plane_dy5(i);
+    return s;
+}
+constexpr int kFWRows = wrow_base5(34);      // 340
+static_assert(kFWRows == 340 && plane_dy5(plane5(3, -2)) == 3 && plane_dy5(plane5(0, 4)) == 0 && plane_dy5(plane5(4, 0)) == 4, "fused weight layout");
+constexpr size_t kFusedWBytes = 16 + (size_t)kFWRows * kFW * sizeof(float) + 16;   // 16 B of zeros either side: column -4 / +131 reads
+constexpr size_t kFusedSmem = kFusedWBytes + 2 * (size_t)kFYR * kFYP * sizeof(double);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t cluster_map(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+template <int kFPY>
+__global__ void __launch_bounds__(fused_threads(kFPY), 1)
+rw_fused_kernel(const float* __restrict__ W, const double* __restrict__ inv_s, const float* __restrict__ x,
+                const float* __restrict__ edge, float* __restrict__ out, const int* __restrict__ chan_off, int totc, int h, int w,
+                int pitch, int n_iter) {
+    constexpr int kFThreads = fused_threads(kFPY);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_w = (float*)(smem_raw + 16);
+    double* s_y = (double*)(smem_raw + kFusedWBytes);   // [2][kFYR][kFYP]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
+    const int n_clusters = gridDim.x / csize, cid = blockIdx.x / csize;
+    const int per = (totc + n_clusters - 1) / n_clusters;
+    const int c_lo = cid * per, c_hi = c_lo + per < totc ? c_lo + per : totc;
+    const int r0 = rank * kFR;
+    const bool active = r0 < h;            // CTAs below the image only take part in the barriers
+    const int col = (warp & 3) * 32 + lane;
+    const int ty0 = (warp >> 2) * kFPY;
+    const size_t plane_sz = (size_t)h * pitch;
+    const size_t hw = (size_t)h * w;
+
+    // zero the pads and both state buffers once: halo rows outside the image, pad columns and rows >= h stay zero for good
+    if (tid < 4) {
+        ((float*)smem_raw)[tid] = 0.f;
+        ((float*)(smem_raw + kFusedWBytes - 16))[tid] = 0.f;
+    }
+    for (int i = tid; i < 2 * kFYR * kFYP; i += kFThreads) s_y[i] = 0.0;
+    __syncthreads();
+    cluster_sync_all();                    // nobody pushes halo rows into a buffer that is still being zeroed
+
+    const uint32_t sy_addr = smem_u32(s_y);
+    const uint32_t up_addr = rank > 0 ? cluster_map(sy_addr, (uint32_t)(rank - 1)) : 0u;
+    const uint32_t dn_addr = rank + 1 < csize ? cluster_map(sy_addr, (uint32_t)(rank + 1)) : 0u;
+
+    int cur_img = -1;
+    constexpr int kRegPlanes = kFPY == 4 ? IRN_RW_REGPLANES4 : IRN_RW_REGPLANES2;   // planes whose forward weights live in registers
+    float wf[kFPY][kRegPlanes > 0 ? kRegPlanes : 1];
+    for (int c = c_lo; c < c_hi; ++c) {
+        int img = 0;
+        while (chan_off[img + 1] <= c) ++img;
+        double val[kFPY], is[kFPY];
+        if (active) {
+            if (img != cur_img) {          // (the last step's barrier ordered every read of the previous weights before this)
+                const float* Wi = W + (size_t)img * 34 * plane_sz;
+                static_for<0, 34>([&](auto K) {
+                    constexpr int k = decltype(K)::value;
+                    constexpr int dyk = plane_dy5(k);
+                    constexpr int rows = kFR + dyk;
+                    float* dst = s_w + (size_t)wrow_base5(k) * kFW;
+                    const float* src = Wi + (size_t)k * plane_sz;
+                    for (int i = tid; i < rows * (kFW / 4); i += kFThreads) {
+                        const int lr = i / (kFW / 4), c4 = (i % (kFW / 4)) * 4;
+                        const int gr = r0 - dyk + lr;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (gr >= 0 && gr < h && c4 < w) {
+                            v = __ldg(reinterpret_cast<const float4*>(src + (size_t)gr * pitch + c4));   // pitch % 4 == 0
+                            if (c4 + 1 >= w) v.y = 0.f;    // the pitch padding is uninitialised workspace
+                            if (c4 + 2 >= w) v.z = 0.f;
+                            if (c4 + 3 >= w) v.w = 0.f;
+                        }
+                        *reinterpret_cast<float4*>(dst + lr * kFW + c4) = v;
+                    }
+                });
+            }
+            if (img != cur_img) {          // forward-tap weights of this thread's pixels stay in registers for the whole walk:
+                __syncthreads();           // shared memory then serves only the mirrored taps (half of the weight reads)
+                static_for<0, kRegPlanes>([&](auto K) {
+                    constexpr int k = decltype(K)::value;
+#pragma unroll
+                    for (int j = 0; j < kFPY; ++j) wf[j][k] = s_w[(wrow_base5(k) + plane_dy5(k) + ty0 + j) * kFW + col];
+                });
+            }
+#pragma unroll
+            for (int j = 0; j < kFPY; ++j) {
+                const int gr = r0 + ty0 + j;
+                const bool in = gr < h && col < w;
+                is[j] = in ? inv_s[(size_t)img * plane_sz + (size_t)gr * pitch + col] : 0.0;
+                // y0 = x * (1 - edge) in fp32 (misc/indexing.py:162), widened
+                val[j] = in ? (double)__fmul_rn(x[(size_t)c * hw + (size_t)gr * w + col], 1.0f - edge[(size_t)img * hw + (size_t)gr * w + col]) : 0.0;
+            }
+        }
+        cur_img = img;
+
+        for (int t = 0; t <= n_iter; ++t) {
+            // publish val (y_t) into buffer t&1: own rows locally, boundary rows into the neighbours' halo rows
+            if (active) {
+                const uint32_t boff = (uint32_t)((t & 1) * kFYR * kFYP * sizeof(double));
+                double* sn = s_y + (t & 1) * kFYR * kFYP;
+#pragma unroll
+                for (int j = 0; j < kFPY; ++j) {
+                    const int lr = ty0 + j;
+                    sn[(kR + lr) * kFYP + kR + col] = val[j];
+                    if (lr < kR) {
+                        if (rank > 0) st_cluster_f64(up_addr + boff + (uint32_t)(((kFR + kR + lr) * kFYP + kR + col) * sizeof(double)), val[j]);
+                    }
+                    if (lr >= kFR - kR) {
+                        if (rank + 1 < csize) st_cluster_f64(dn_addr + boff + (uint32_t)(((lr - (kFR - kR)) * kFYP + kR + col) * sizeof(double)), val[j]);
+                    }
+                }
+            }
+            cluster_sync_all();
+            if (t == n_iter) break;
+            if (active) {
+                const double* sy = s_y + (t & 1) * kFYR * kFYP;
+                double acc[kFPY];
+#pragma unroll
+                for (int j = 0; j < kFPY; ++j) acc[j] = val[j];   // diagonal weight 1
+                static_for<0, 5>([&](auto CLS) {
+                    constexpr int cls = decltype(CLS)::value;
+                    static_for<0, (cls == 0 ? 1 : 2)>([&](auto SGN) {
+                        constexpr int dxc = decltype(SGN)::value == 0 ? cls : -cls;
+                        static_for<-kR, kFPY + kR>([&](auto RR) {
+                            constexpr int r = decltype(RR)::value;
+                            const double v = sy[(kR + ty0 + r) * kFYP + kR + col + dxc];
+                            static_for<0, kFPY>([&](auto JJ) {
+                                constexpr int j = decltype(JJ)::value;
+                                constexpr int dy = r - j;
+                                constexpr int kf = plane5(dy, dxc);
+                                constexpr int kb = plane5(-dy, -dxc);
+                                if constexpr (kf >= 0) {          // forward tap: W_kf at the pixel itself (register copy)
+                                    if constexpr (kf < kRegPlanes) acc[j] = fma(widen_weight(wf[j][kf]), v, acc[j]);
+                                    else acc[j] = fma(widen_weight(s_w[(wrow_base5(kf) + dy + ty0 + j) * kFW + col]), v, acc[j]);
+                                } else if constexpr (kb >= 0) {   // mirrored tap: W_kb at the pixel being read, (row ty0+r, col+dxc)
+                                    acc[j] = fma(widen_weight(s_w[(wrow_base5(kb) + ty0 + j) * kFW + col + dxc]), v, acc[j]);
+                                }
+                            });
+                        });
+                    });
+                });
+#pragma unroll
+                for (int j = 0; j < kFPY; ++j) val[j] = acc[j] * is[j];
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < kFPY; ++j) {
+                const int gr = r0 + ty0 + j;
+                if (gr < h && col < w) out[(size_t)c * hw + (size_t)gr * w + col] = (float)val[j];
+            }
+        }
+    }
+    cluster_sync_all();   // no CTA exits while a neighbour may still push into its shared memory
+}
+
 // ---------------------------------------------------------------- workspace carving
 struct RwWorkspace {
     float* W;
@@ -605,11 +815,57 @@ static int launch_tma_steps(const RwWorkspace& ws, int n_img, int totc, int h, i
     return kOk;
 }
 
+// Launches the fused walk; *launched = false when the device cannot co-schedule a cluster of the needed size (caller falls
+// back to the per-step kernel).
+template <int PY>
+static int launch_fused(const RwWorkspace& ws, const float* x, const float* edge, float* out, int totc, int h, int w, int n_iter,
+                        cudaStream_t stream, bool* launched, int* n_clusters_out) {
+    *launched = false;
+    const int need = (h + kFR - 1) / kFR;
+    int cs = 1;
+    while (cs < need) cs *= 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        IRN_CUDA(cudaFuncSetAttribute(rw_fused_kernel<PY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
+        IRN_CUDA(cudaFuncSetAttribute(rw_fused_kernel<PY>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)cs);
+    cfg.blockDim = dim3(fused_threads(PY));
+    cfg.dynamicSmemBytes = kFusedSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, rw_fused_kernel<PY>, &cfg) != cudaSuccess || max_clusters <= 0) {
+        cudaGetLastError();   // not an error of this call: the step kernel takes over
+        return kOk;
+    }
+    const int n_clusters = totc < max_clusters ? totc : max_clusters;
+    cfg.gridDim = dim3((unsigned)(n_clusters * cs));
+    const float* Wp = ws.W;
+    const double* isp = ws.inv_s;
+    const int* cop = ws.chan_off;
+    int pitch = ws.pitch;
+    IRN_CUDA(cudaLaunchKernelEx(&cfg, rw_fused_kernel<PY>, Wp, isp, x, edge, out, cop, totc, h, w, pitch, n_iter));
+    IRN_LAUNCH_CHECK("rw_fused_kernel");
+    *launched = true;
+    *n_clusters_out = n_clusters;
+    return kOk;
+}
+
 // Optional device timing of the step kernels (bench.py roofline): events recorded on the caller's stream around the
 // n_iter step launches of the most recent walk on this thread.
 static thread_local bool g_rw_timing = false;
 static thread_local cudaEvent_t g_rw_ev[2] = {nullptr, nullptr};
 static thread_local int g_rw_timed_iters = 0;
+static thread_local int g_rw_last_fused = 0;   // clusters of the last fused launch, 0 = ran step by step
 
 static int walk_impl(const float* x, const float* edge, float* out, int n_img, const int32_t* chan_offsets, int h, int w,
                      int radius, double beta, int n_iter, void* workspace, size_t workspace_bytes, int variant,
@@ -650,6 +906,30 @@ static int walk_impl(const float* x, const float* edge, float* out, int n_img, c
     dim3 pgrid((unsigned)((hw + 255) / 256), n_img);
     rw_rowsum_kernel<<<pgrid, 256, 0, stream>>>(ws.W, ws.inv_s, h, w, pitch);
     IRN_LAUNCH_CHECK("rw_rowsum_kernel");
+    // variant 0: fused cluster kernel when the grid fits (h, w <= 128), else the per-step TMA kernel; 2 forces the per-step
+    // kernel, 4 the fused one
+    bool fused = false;
+    int n_fused_clusters = 0;
+    if (radius == 5 && (variant == 0 || variant == 4 || variant == 5) && h <= kFR * 16 && w <= kFW) {
+        if (g_rw_timing) {
+            if (!g_rw_ev[0]) {
+                IRN_CUDA(cudaEventCreate(&g_rw_ev[0]));
+                IRN_CUDA(cudaEventCreate(&g_rw_ev[1]));
+            }
+            IRN_CUDA(cudaEventRecord(g_rw_ev[0], stream));
+        }
+        rc = variant == 5 ? launch_fused<2>(ws, x, edge, out, totc, h, w, n_iter, stream, &fused, &n_fused_clusters)
+                          : launch_fused<4>(ws, x, edge, out, totc, h, w, n_iter, stream, &fused, &n_fused_clusters);
+        if (rc) return rc;
+        if (fused && g_rw_timing) {
+            IRN_CUDA(cudaEventRecord(g_rw_ev[1], stream));
+            g_rw_timed_iters = n_iter > 0 ? n_iter : 1;
+        }
+    }
+    if ((variant == 4 || variant == 5) && !fused) return fail(kUnsupported, "irn_random_walk: fused walk needs radius 5, h <= %d, w <= %d and a device that can co-schedule the cluster", kFR * 16, kFW);
+    g_rw_last_fused = fused ? n_fused_clusters : 0;
+    if (fused) return kOk;
+
     rw_init_kernel<<<pgrid, 256, 0, stream>>>(x, edge, ws.y[0], ws.chan_off, h, w, pitch);
     IRN_LAUNCH_CHECK("rw_init_kernel");
 
@@ -713,6 +993,8 @@ extern "C" size_t irn_rw_workspace_bytes(int n_img, int h, int w, int total_chan
 
 extern "C" int irn_rw_last_launch_count(void) { return launch_counter(); }
 
+extern "C" int irn_rw_last_was_fused(void) { return g_rw_last_fused; }
+
 extern "C" int irn_rw_set_timing(int enable) {
     g_rw_timing = enable != 0;
     return kOk;
@@ -735,9 +1017,9 @@ extern "C" int irn_random_walk(const float* x, const float* edge, float* out, in
     return walk_impl(x, edge, out, n_img, chan_offsets, h, w, radius, beta, n_iter, workspace, workspace_bytes, 0, (cudaStream_t)stream);
 }
 
-// variant: 0 = production path (TMA-staged register-window step kernel, radius 5), 1 = generic bounds-checked kernel
-// (validation), 3 = persistent one-CTA-per-SM TMA-ring kernel (experiment: 67 vs 50 us/step at C=2 -- four consumer warps
-// per SM cannot hide the LDS -> widen -> DFMA latency; kept for A/B measurements)
+// variant: 0 = production (fused cluster kernel when h,w <= 128, else the per-step TMA kernel), 1 = generic bounds-checked
+// kernel (validation), 2 = per-step TMA kernel, 3 = persistent one-CTA-per-SM TMA-ring step kernel (experiment: 67 vs 50
+// us/step at C=2; kept for A/B measurements), 4 = fused cluster kernel or kUnsupported
 extern "C" int irn_random_walk_variant(const float* x, const float* edge, float* out, int n_img, const int32_t* chan_offsets,
                                        int h, int w, int radius, double beta, int n_iter, void* workspace,
                                        size_t workspace_bytes, int variant, irn_stream_t stream) {

@@ -112,6 +112,11 @@ def random_walk_batch(x, edge, chan_offsets, radius=5, beta=10, n_iter=256, vari
     return out
 
 
+def last_walk_was_fused():
+    """True when the last walk on this thread ran as the fused cluster kernel (one launch for all steps)."""
+    return bool(_lib.lib().irn_rw_last_was_fused())
+
+
 def propagate_to_edge(x, edge, radius=5, beta=10, exp_times=8):
     """misc/indexing.py:141-167.  x: cuda fp32, any shape ending in (h,w); edge cuda fp32
     [1,h,w].  Returns [C,1,h,w] with C = prod(x.shape[:-2])."""

@@ -29,7 +29,7 @@ def preprocess_batch(images_u8, scales=(1.0, 0.5, 1.5, 2.0), pin=True):
 
 class PseudoLabelPipeline:
     def __init__(self, cam_model, irn_model, device, scales=(1.0, 0.5, 1.5, 2.0), beta=10, exp_times=8, bg_thres=0.25,
-                 cam_sub_batch=8, rw_sub_batch=24):
+                 cam_sub_batch=8, rw_sub_batch=64):
         self.cam, self.irn, self.device = cam_model, irn_model, device
         self.scales, self.beta, self.exp_times, self.bg = scales, beta, exp_times, bg_thres
         self.cam_sub, self.rw_sub = cam_sub_batch, rw_sub_batch
@@ -96,7 +96,7 @@ class PseudoLabelPipeline:
             e, _ = self.irn.forward_batch(x1[2 * i:2 * min(i + irn_sub, N)])
             edges.append(e[:, 0])
         edges = torch.cat(edges, 0)
-        # ---- R1-R6: batched walk (sub-batches sized so the weights stay L2-resident)
+        # ---- R1-R6: batched walk (the fused cluster kernel takes every (image, class) of the sub-batch in one launch)
         counts = [int(s.shape[0]) for s in strided]
         rws = []
         for i in range(0, N, self.rw_sub):

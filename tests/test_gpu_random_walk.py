@@ -33,7 +33,7 @@ def test_edge_to_affinity_exact(cuda_dev):
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(golden_path("rw_*.npz"))), ids=os.path.basename)
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_random_walk_vs_reference(cuda_dev, path, variant):
     g = np.load(path)
     x, edge = g["x"], g["edge"]
@@ -57,16 +57,28 @@ def test_propagate_to_edge_signature(cuda_dev):
     assert torch.allclose(rw4[0::2], rw, atol=1e-6) and torch.allclose(rw4[1::2], 0.5 * rw, atol=1e-6)
 
 
-@pytest.mark.parametrize("h,w", [(1, 1), (3, 50), (17, 31), (128, 128), (125, 94)])
+@pytest.mark.parametrize("h,w", [(1, 1), (3, 50), (8, 128), (9, 5), (17, 31), (33, 127), (64, 64), (65, 40), (128, 128), (125, 94),
+                                 (129, 60), (40, 130)])
 def test_walk_shapes_and_properties(cuda_dev, h, w):
-    """Ragged / tiny / full-size grids: production kernel == generic kernel == fp64 oracle; convexity."""
+    """Ragged / tiny / full-size grids: fused cluster kernel (every cluster size 1..16) == step kernels == generic kernel ==
+    fp64 oracle; convexity.  Grids beyond 128 fall back to the per-step kernel."""
     C = 3
     e = synth.edge_map(h, w, "uniform", h + w)
     x = synth.seeds(C, h, w, h)
-    a = indexing.random_walk_batch(_t(x, cuda_dev), _t(e, cuda_dev), [0, C], n_iter=16, variant=0).cpu().numpy()
-    b = indexing.random_walk_batch(_t(x, cuda_dev), _t(e, cuda_dev), [0, C], n_iter=16, variant=1).cpu().numpy()
-    c = indexing.random_walk_batch(_t(x, cuda_dev), _t(e, cuda_dev), [0, C], n_iter=16, variant=3).cpu().numpy()
-    assert np.abs(a - b).max() < 1e-6 and np.array_equal(a, c)   # ring and two-buffer kernels do identical arithmetic
+    run = lambda v, n=16: indexing.random_walk_batch(_t(x, cuda_dev), _t(e, cuda_dev), [0, C], n_iter=n, variant=v).cpu().numpy()
+    a = run(0)
+    fits = h <= 128 and w <= 128
+    assert indexing.last_walk_was_fused() == fits
+    b, s2, c = run(1), run(2), run(3)
+    assert np.abs(a - b).max() < 1e-6
+    assert np.array_equal(a, s2) and np.array_equal(a, c)   # fused, two-buffer and ring kernels do identical arithmetic
+    if fits:
+        assert np.array_equal(a, run(4)) and np.array_equal(a, run(5))
+        for n in (0, 1, 3):   # odd / zero step counts exercise both state buffers
+            assert np.array_equal(run(4, n), run(2, n))
+    else:
+        with pytest.raises(Exception):
+            run(4)
     truth = oi.propagate_stencil(x, e, 5, 10, 16).reshape(C, h, w)
     assert np.abs(a - truth).max() < 1e-6
     x0 = x * (1 - e)
