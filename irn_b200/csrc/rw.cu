@@ -910,7 +910,24 @@ static int walk_impl(const float* x, const float* edge, float* out, int n_img, c
     // kernel, 4 the fused one
     bool fused = false;
     int n_fused_clusters = 0;
-    if (radius == 5 && (variant == 0 || variant == 4 || variant == 5) && h <= kFR * 16 && w <= kFW) {
+    bool want_fused = radius == 5 && (variant == 0 || variant == 4 || variant == 5) && h <= kFR * 16 && w <= kFW;
+    if (want_fused && variant == 0) {
+        // Both kernels give bit-identical results; pick the faster one from B200 measurements (profiles/r01_rw_fused.md):
+        // the fused kernel walks one (image, class) per cluster at ~2.85 us per step on the ~7 clusters that fit; the per-step
+        // kernel shares the weight reads between up to 4 classes of an image (~0.54 + 0.15 C us per image-chunk per step once
+        // the grid fills the GPU, ~9 us per step at least).  Single-class images favour the fused kernel, large batches of
+        // many-class images (instance path: classes x instances) the per-step one.
+        double step_us = 0.0;
+        for (int i = 0; i < n_img; ++i) {
+            int c = chan_offsets[i + 1] - chan_offsets[i];
+            for (; c > 0; c -= 4) step_us += 0.54 + 0.15 * (c < 4 ? c : 4);
+        }
+        step_us *= (double)h * w / (128.0 * 128.0);
+        if (step_us < 9.0) step_us = 9.0;
+        const double fused_us = 2.85 * ((totc + 6) / 7);
+        want_fused = fused_us <= step_us;
+    }
+    if (want_fused) {
         if (g_rw_timing) {
             if (!g_rw_ev[0]) {
                 IRN_CUDA(cudaEventCreate(&g_rw_ev[0]));

@@ -103,6 +103,19 @@ def test_walk_batch_mixed_channels(cuda_dev):
         assert np.abs(one - truth).max() < 1e-6
 
 
+def test_walk_dispatch_many_channels(cuda_dev):
+    """Instance-path shape (classes x instances = many channels per image): variant 0 picks the per-step kernel, which shares
+    the weight reads between 4 channels; the fused kernel gives the same bits."""
+    h, w, C = 64, 64, 40
+    e = synth.edge_map(h, w, "bimodal", 7)
+    x = synth.seeds(C, h, w, 7)
+    a = indexing.random_walk_batch(_t(x, cuda_dev), _t(e, cuda_dev), [0, C], n_iter=8, variant=0).cpu().numpy()
+    assert not indexing.last_walk_was_fused()
+    b = indexing.random_walk_batch(_t(x, cuda_dev), _t(e, cuda_dev), [0, C], n_iter=8, variant=4).cpu().numpy()
+    assert indexing.last_walk_was_fused()
+    assert np.array_equal(a, b)
+
+
 def test_walk_linearity_and_fixed_point(cuda_dev):
     h, w = 64, 64
     e = synth.edge_map(h, w, "bimodal", 3)
