@@ -200,6 +200,35 @@ int irn_instance_seeds(const float* cams, const int32_t* instance_map, int K, in
 int irn_segment_stats(const int32_t* labels, const int32_t* index, const float* scores, int H, int W,
                       int32_t* area, int32_t* max_bits, irn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * C1  multi-scale input preparation on the device.  Replaces, for a decoded uint8 image, the per-scale body of
+ * VOC12ClassificationDatasetMSF.__getitem__ (voc12/dataloader.py:191-201): imutils.pil_rescale
+ * (misc/imutils.py:8-22 -> Pillow BICUBIC resize of the uint8 image), TorchvisionNormalize
+ * (voc12/dataloader.py:65-78), HWC->CHW and the stack with the W-flip.  Integer / table arithmetic: bit-exact
+ * with Pillow's 8-bit resampler (two passes, horizontal first, 22-bit fixed-point coefficients) and numpy's
+ * float64 normalisation rounded once to fp32.
+ *
+ * irn_resize_ksize / irn_resize_coeffs   (host) Pillow's coefficient table of one axis: bounds int32 [out,2]
+ *                         (first source index, tap count), kk int32 [out, ksize] (2^22 fixed point).
+ * irn_normalize_lut       (host) fp32 [3][256]: ((u/255 - mean[c]) / std[c]) evaluated in double.
+ * irn_resize_plan_*       a plan owns the two coefficient tables and the normalisation table on the current device
+ *                         for one (H, W) -> (out_h, out_w) pair (out == in on an axis skips that pass, like Pillow).
+ * irn_resize_forward      img: device uint8 [B,H,W,3].  out (optional): device fp32 [2B,3,out_h,out_w], image b at
+ *                         rows 2b (as is) and 2b+1 (W-flipped) = the [2,3,h,w] tensors the networks take.
+ *                         out_u8 (optional): device uint8 [B,out_h,out_w,3], the resized image itself.
+ *                         workspace >= irn_resize_workspace_bytes(plan, B) (the 8-bit intermediate image).
+ */
+typedef struct irn_resize_plan irn_resize_plan;
+int irn_resize_ksize(int in_size, int out_size);
+int irn_resize_coeffs(int in_size, int out_size, int32_t* bounds, int32_t* kk);
+int irn_normalize_lut(const double* mean3, const double* std3, float* lut768);
+int irn_resize_plan_create(int H, int W, int out_h, int out_w, const double* mean3, const double* std3,
+                           irn_resize_plan** out);
+int irn_resize_plan_destroy(irn_resize_plan* plan);
+size_t irn_resize_workspace_bytes(const irn_resize_plan* plan, int B);
+int irn_resize_forward(const irn_resize_plan* plan, const uint8_t* img, int B, float* out, uint8_t* out_u8,
+                       void* workspace, size_t workspace_bytes, irn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

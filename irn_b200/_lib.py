@@ -53,6 +53,13 @@ SIGNATURES = {
     "irn_segment_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "irn_rw_labels": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p]),
+    "irn_resize_ksize": (c_int, [c_int, c_int]),
+    "irn_resize_coeffs": (c_int, [c_int, c_int, c_void_p, c_void_p]),
+    "irn_normalize_lut": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "irn_resize_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, ctypes.POINTER(c_void_p)]),
+    "irn_resize_plan_destroy": (c_int, [c_void_p]),
+    "irn_resize_workspace_bytes": (c_size_t, [c_void_p, c_int]),
+    "irn_resize_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 

@@ -7,7 +7,7 @@ device end to end (the reference round-trips every image through a .npy file and
 import numpy as np
 import torch
 
-from . import cam_ops, indexing
+from . import cam_ops, indexing, preprocess
 from .voc12 import dataloader as voc_data
 
 
@@ -37,6 +37,31 @@ class PseudoLabelPipeline:
         self._staging = {}
         if 1.0 not in scales:
             raise ValueError("the IRNet pass uses the scale-1.0 input (step/make_sem_seg_labels.py:64-66)")
+
+    @torch.no_grad()
+    def run_u8(self, images_u8, labels, want_highres=True):
+        """Same as run(), starting from decoded images: uint8 [N,H,W,3], cuda or (pinned) host.  The per-scale bicubic
+        rescale, normalisation and flip stack of the reference's loader (voc12/dataloader.py:191-201) run on the device,
+        bit-exact (irn_b200.preprocess), so a step uploads 0.79 MB per 512x512 image instead of 47 MB of fp32 pyramids."""
+        dev = self.device
+        x = images_u8
+        if not x.is_cuda:
+            buf = self._staging.get("u8")
+            if buf is None or buf.shape != x.shape:
+                buf = torch.empty(x.shape, dtype=torch.uint8, device=dev)
+                self._staging["u8"] = buf
+            buf.copy_(x, non_blocking=True)
+            x = buf
+        N, H, W = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+        inputs = []
+        for k, s in enumerate(self.scales):
+            oh, ow = (H, W) if s == 1 else preprocess.rescaled_size(H, W, s)
+            buf = self._staging.get(k)
+            if buf is None or tuple(buf.shape) != (2 * N, 3, oh, ow):
+                buf = torch.empty((2 * N, 3, oh, ow), dtype=torch.float32, device=dev)
+                self._staging[k] = buf
+            inputs.append(preprocess.resize_normalize(x, (oh, ow), out=buf))
+        return self.run(inputs, labels, (H, W), want_highres)
 
     @torch.no_grad()
     def run(self, inputs, labels, size, want_highres=True):

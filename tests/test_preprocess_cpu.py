@@ -1,0 +1,56 @@
+"""C1 pre-processing, CPU side: the oracle's restatement of Pillow's 8-bit bicubic resampler against the installed
+Pillow (the third-party code misc/imutils.py:8-22 calls), the normalisation table against TorchvisionNormalize, and
+the C ABI's host-side coefficient / table functions against the oracle.  All integer / table work: exact equality."""
+import numpy as np
+import pytest
+from PIL import Image
+
+from irn_b200 import preprocess, synth
+from irn_b200.voc12 import dataloader as dl
+from oracle import resize as R
+
+SIZES = [(512, 512, 256, 256), (512, 512, 768, 768), (512, 512, 1024, 1024), (375, 500, 188, 250), (375, 500, 562, 750),
+         (375, 500, 750, 1000), (333, 500, 166, 250), (500, 281, 250, 140), (7, 5, 14, 10), (16, 16, 8, 8), (100, 37, 51, 74),
+         (3, 3, 1, 1), (2, 9, 5, 4), (64, 64, 64, 96), (64, 64, 32, 64)]
+
+
+@pytest.mark.parametrize("H,W,oh,ow", SIZES)
+def test_oracle_resize_equals_pillow(H, W, oh, ow):
+    rng = np.random.default_rng(H * 1000 + W)
+    for img in (rng.integers(0, 256, (H, W, 3), dtype=np.uint8), synth.image(3, H, W)):
+        ref = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BICUBIC))
+        assert np.array_equal(R.pil_bicubic_resize_u8(img, oh, ow), ref)
+
+
+def test_oracle_resize_random_size_pairs():
+    rng = np.random.default_rng(7)
+    for _ in range(120):
+        H, W = (int(v) for v in rng.integers(1, 160, 2))
+        oh, ow = (int(v) for v in rng.integers(1, 240, 2))
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BICUBIC))
+        assert np.array_equal(R.pil_bicubic_resize_u8(img, oh, ow), ref), (H, W, oh, ow)
+
+
+def test_oracle_msf_equals_reference_loader_body():
+    img = synth.image(5, 375, 500)
+    scales = (1.0, 0.5, 1.5, 2.0)
+    for a, b in zip(dl.multi_scale_flip(img, scales), R.msf_preprocess(img, scales)):
+        assert a.dtype == b.dtype == np.float32 and np.array_equal(a, b)
+    norm = dl.TorchvisionNormalize()
+    ramp = np.repeat(np.arange(256, dtype=np.uint8)[:, None, None], 3, 2)
+    assert np.array_equal(norm(ramp)[:, 0].T, R.normalize_lut())
+
+
+@pytest.mark.parametrize("n_in,n_out", [(512, 256), (512, 768), (512, 1024), (375, 188), (500, 250), (375, 562), (500, 1000),
+                                        (7, 14), (5, 10), (3, 1), (9, 4), (1, 7), (1000, 3), (333, 166), (281, 140)])
+def test_abi_coefficients_equal_oracle(n_in, n_out):
+    b, k = preprocess.resize_coeffs(n_in, n_out)
+    rb, rk = R.pil_bicubic_coeffs(n_in, n_out)
+    assert b.shape == rb.shape and k.shape == rk.shape
+    assert np.array_equal(b, rb) and np.array_equal(k, rk)
+
+
+def test_abi_lut_equals_oracle():
+    assert np.array_equal(preprocess.normalize_lut(), R.normalize_lut())
+    assert preprocess.rescaled_size(375, 500, 0.5) == R.rescaled_size(375, 500, 0.5) == (188, 250)
