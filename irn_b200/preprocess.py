@@ -64,6 +64,8 @@ _ws = {}
 
 def _plan(dev, H, W, oh, ow, mean, std):
     key = (dev.index, H, W, oh, ow, tuple(mean), tuple(std))
+    if key not in _plans and len(_plans) >= 1024:      # VOC has a few hundred distinct sizes x scales; bound the cache anyway
+        _plans.clear()
     if key not in _plans:
         with torch.cuda.device(dev):
             _plans[key] = _Plan(H, W, oh, ow, mean, std)

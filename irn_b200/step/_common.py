@@ -12,6 +12,7 @@ import torch
 from torch.utils.data import DataLoader
 from torch.utils.data._utils.collate import default_collate
 
+from .. import preprocess
 from ..misc import torchutils
 from ..voc12 import dataloader as voc_data
 
@@ -33,12 +34,29 @@ def progress(process_id, n_gpus, it, n_items):
         print("%d " % ((5 * it + 1) // step), end="", flush=True)
 
 
+def device_pyramid(args):
+    """--device_pyramid (default on): loader workers only decode; the per-scale rescale / normalise / flip stack of
+    voc12/dataloader.py:191-201 is built on the GPU, bit-identical (irn_b200.preprocess)."""
+    return bool(getattr(args, "device_pyramid", True))
+
+
 def make_dataset(args, list_path, scales):
     """VOC images from --voc12_root, or seeded synthetic ones with --synthetic N."""
     if getattr(args, "synthetic", 0):
         names = list_path if os.path.exists(list_path) else None
-        return voc_data.SyntheticMSF(int(args.synthetic), scales=scales, name_list=names)
-    return voc_data.VOC12ClassificationDatasetMSF(list_path, voc12_root=args.voc12_root, scales=scales)
+        return voc_data.SyntheticMSF(int(args.synthetic), scales=scales, name_list=names, decode_only=device_pyramid(args))
+    return voc_data.VOC12ClassificationDatasetMSF(list_path, voc12_root=args.voc12_root, scales=scales,
+                                                  decode_only=device_pyramid(args))
+
+
+def attach_pyramid(pack, scales):
+    """Turn a decode-only item into what the reference's loader yields: pack['img'] = [1,2,3,h,w] per scale (a single
+    tensor when there is one scale, voc12/dataloader.py:200-201), already on the current device."""
+    if "img_u8" not in pack:
+        return pack
+    pyr = preprocess.msf_batch(pack["img_u8"].cuda(non_blocking=True), scales)
+    pack["img"] = pyr[0][None] if len(scales) == 1 else [p[None] for p in pyr]
+    return pack
 
 
 def work_loop(process_id, model, dataset, args, per_image):
@@ -49,8 +67,9 @@ def work_loop(process_id, model, dataset, args, per_image):
     loader = DataLoader(shard, shuffle=False, num_workers=args.num_workers // max(n_gpus, 1), pin_memory=False, collate_fn=collate_one)
     with torch.no_grad(), torch.cuda.device(process_id):
         model.cuda()
+        scales = getattr(getattr(shard, "dataset", shard), "scales", (1.0,))
         for it, pack in enumerate(loader):
-            per_image(model, pack, args)
+            per_image(model, attach_pyramid(pack, scales), args)
             progress(process_id, n_gpus, it, len(shard))
 
 

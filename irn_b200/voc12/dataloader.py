@@ -71,7 +71,8 @@ class VOC12ClassificationDatasetMSF(Dataset):
     "size": (H, W), "label": FloatTensor[20]}."""
 
     def __init__(self, img_name_list_path, voc12_root, img_normal=TorchvisionNormalize(), scales=(1.0,),
-                 cls_labels_path="voc12/cls_labels.npy"):
+                 cls_labels_path="voc12/cls_labels.npy", decode_only=False):
+        self.decode_only = decode_only      # hand over the decoded uint8 image; the pyramid is built on the device
         self.img_name_list = load_img_name_list(img_name_list_path)
         self.voc12_root = voc12_root
         self.img_normal = img_normal
@@ -85,17 +86,22 @@ class VOC12ClassificationDatasetMSF(Dataset):
     def __getitem__(self, idx):
         name_str = decode_int_filename(self.img_name_list[idx])
         img = np.asarray(Image.open(get_img_path(name_str, self.voc12_root)).convert("RGB"))
-        return {"name": name_str, "img": multi_scale_flip(img, self.scales, self.img_normal),
-                "size": (img.shape[0], img.shape[1]), "label": torch.from_numpy(self.label_list[idx])}
+        out = {"name": name_str, "size": (img.shape[0], img.shape[1]), "label": torch.from_numpy(self.label_list[idx])}
+        if self.decode_only:
+            out["img_u8"] = np.ascontiguousarray(img)
+        else:
+            out["img"] = multi_scale_flip(img, self.scales, self.img_normal)
+        return out
 
 
 class SyntheticMSF(Dataset):
     """Same item format as VOC12ClassificationDatasetMSF over seeded synthetic images (irn_b200.synth):
     ids are taken from an image-name list when given, else 2007_000000 + index."""
 
-    def __init__(self, n_items, size=(512, 512), scales=(1.0,), name_list=None, img_normal=TorchvisionNormalize()):
+    def __init__(self, n_items, size=(512, 512), scales=(1.0,), name_list=None, img_normal=TorchvisionNormalize(), decode_only=False):
         from .. import synth
         self.synth = synth
+        self.decode_only = decode_only
         self.n, self.size, self.scales, self.img_normal = n_items, size, scales, img_normal
         self.names = None if name_list is None else load_img_name_list(name_list)[:n_items]
 
@@ -105,5 +111,9 @@ class SyntheticMSF(Dataset):
     def __getitem__(self, idx):
         name = decode_int_filename(self.names[idx]) if self.names is not None else "2007_%06d" % idx
         img = self.synth.image(idx, *self.size)
-        return {"name": name, "img": multi_scale_flip(img, self.scales, self.img_normal), "size": tuple(self.size),
-                "label": torch.from_numpy(self.synth.label(idx))}
+        out = {"name": name, "size": tuple(self.size), "label": torch.from_numpy(self.synth.label(idx))}
+        if self.decode_only:
+            out["img_u8"] = img
+        else:
+            out["img"] = multi_scale_flip(img, self.scales, self.img_normal)
+        return out

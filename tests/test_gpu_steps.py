@@ -56,6 +56,23 @@ def test_make_cam_outputs(voc_tree):
         assert np.abs(d["high_res"] - g["cam_high%d" % i]).max() < 1e-4
 
 
+def test_make_cam_host_pyramid_identical(voc_tree):
+    """--device_pyramid False (PIL pyramids built by the loader, the reference's data path) writes the same bytes."""
+    g, ids, args = voc_tree
+    from irn_b200.step import make_cam
+    host_args = types.SimpleNamespace(**vars(args))
+    host_args.device_pyramid = False
+    host_args.cam_out_dir = os.path.join(os.path.dirname(args.cam_out_dir), "cam_host")
+    os.makedirs(host_args.cam_out_dir, exist_ok=True)
+    make_cam.run(host_args)
+    make_cam.run(args)
+    for name in ids:
+        a = np.load(os.path.join(args.cam_out_dir, name + ".npy"), allow_pickle=True).item()
+        b = np.load(os.path.join(host_args.cam_out_dir, name + ".npy"), allow_pickle=True).item()
+        assert np.array_equal(a["keys"].numpy(), b["keys"].numpy())
+        assert np.array_equal(a["cam"].numpy(), b["cam"].numpy()) and np.array_equal(a["high_res"], b["high_res"])
+
+
 def test_make_sem_seg_labels_outputs(voc_tree):
     g, ids, args = voc_tree
     from irn_b200.step import make_sem_seg_labels

@@ -15,11 +15,15 @@ LAYERS = [  # name, cin, cout, k, stride, H(in), B, residual
     ("L4 c2 3x3 512", 512, 512, 3, 1, 64, 16, False),
     ("L4 c3 512->2048 +res", 512, 2048, 1, 1, 64, 16, True),
     ("L4 c1 2048->512", 2048, 512, 1, 1, 64, 16, False),
+    ("L2 c1 512->128", 512, 128, 1, 1, 128, 16, False),
+    ("L2 ds 256->512 s2", 256, 512, 1, 2, 256, 16, False),
+    ("L3 c1 512->256", 512, 256, 1, 1, 128, 16, False),
+    ("L3 ds 512->1024 s2", 512, 1024, 1, 2, 128, 16, False),
 ]
 dev = torch.device("cuda:0")
 only = os.environ.get("CONV_ONLY")
 if only:
-    LAYERS = [l for l in LAYERS if only in l[0]]
+    LAYERS = [l for l in LAYERS if any(o in l[0] for o in only.split(','))]
 for name, cin, cout, k, s, H, B, res in LAYERS:
     w = (torch.randn(cout, cin, k, k) * (2.0 / (cin * k * k)) ** 0.5).numpy()
     bn = [np.ones(cout, np.float32), np.zeros(cout, np.float32), np.zeros(cout, np.float32), np.ones(cout, np.float32)]
