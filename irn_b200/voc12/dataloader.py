@@ -88,7 +88,7 @@ class VOC12ClassificationDatasetMSF(Dataset):
         img = np.asarray(Image.open(get_img_path(name_str, self.voc12_root)).convert("RGB"))
         out = {"name": name_str, "size": (img.shape[0], img.shape[1]), "label": torch.from_numpy(self.label_list[idx])}
         if self.decode_only:
-            out["img_u8"] = np.ascontiguousarray(img)
+            out["img_u8"] = np.array(img)            # writable copy: torch's collate wraps it without a warning
         else:
             out["img"] = multi_scale_flip(img, self.scales, self.img_normal)
         return out
@@ -113,7 +113,7 @@ class SyntheticMSF(Dataset):
         img = self.synth.image(idx, *self.size)
         out = {"name": name, "size": tuple(self.size), "label": torch.from_numpy(self.synth.label(idx))}
         if self.decode_only:
-            out["img_u8"] = img
+            out["img_u8"] = np.array(img)
         else:
             out["img"] = multi_scale_flip(img, self.scales, self.img_normal)
         return out
