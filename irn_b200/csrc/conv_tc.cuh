@@ -92,6 +92,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
 // STAGES: smem pipeline depth.  NACC: 3 = two alternating hi*hi accumulators + one for the cross terms; 2 = one hi*hi + cross
 // (short K: few accumulation steps, and 2 x BN TMEM columns let several CTAs share an SM so their fixed latencies overlap).
 template <int BN, int STAGES, int NACC>
@@ -302,16 +312,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
 //   warp 0      TMA producer, runs ahead through the smem ring across tile boundaries
 //   warps 2-5   hi/lo split of the activation k-blocks
 //   warp 1      MMA issuer; two TMEM accumulator sets (hi*hi | cross terms each) ping-pong between consecutive tiles
-//   warps 6-9   epilogue: TMEM -> shared staging -> coalesced (+bias +residual, ReLU) stores, overlapped with the next
-//               tile's loads and MMAs; the residual rows are prefetched before the accumulator is ready
-constexpr int kTcPersistThreads = 320;
+//   warps 6-13  epilogue: TMEM -> shared staging -> coalesced (+bias +residual, ReLU) stores, overlapped with the next
+//               tile's loads and MMAs.  Two warps per TMEM lane quarter, each taking half of the tile's channels: with four
+//               warps the residual rows had to be fetched in two batches of 16 and the second batch's HBM latency (~1 us per
+//               tile, 32 KB in flight per SM) was the critical path of the 1x1 expansion convs; with eight, a warp's whole
+//               32-row x BN/2 slice (64 KB per SM) is in flight before the accumulator is even ready.
+constexpr int kTcPersistThreads = 448;
 
 template <int BN>
 struct TcPersistCfg {
     static constexpr int kStages = BN == 128 ? 2 : 3;
     static constexpr int kStageBytes = 2 * 16384 + 2 * BN * 128;
-    static constexpr int kLd = BN + 4;
-    static constexpr int kStagingBytes = 128 * kLd * 4;
+    static constexpr int kCols = BN / 2;            // channels per epilogue warp
+    static constexpr int kLd = kCols + 4;           // padded staging row (floats): conflict-free float4 rows
+    static constexpr int kStagingBytes = 2 * 128 * kLd * 4;
     static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + kStagingBytes + 256;
     static constexpr int kTmemCols = 4 * BN <= 256 ? 256 : 512;   // 2 sets x (main + cross) x BN columns
 };
@@ -348,7 +362,7 @@ conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);
+            mbar_init(&tmem_empty[i], 8);
         }
         fence_mbar_init();
     }
@@ -448,76 +462,76 @@ conv_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             }
         }
     } else {
-        // ---- epilogue warps 6..9 (TMEM lane quarter = warp % 4)
+        // ---- epilogue warps 6..13: TMEM lane quarter = warp % 4, channel half = (warp - 6) / 4
         const int q = warp & 3;
+        const int hf = (warp - 6) >> 2;
+        constexpr int kCols = Cfg::kCols;
         constexpr int kLd = Cfg::kLd;
-        constexpr int kLanesPerRow = BN / 4;
+        constexpr int kLanesPerRow = kCols / 4;          // 16 (BN=128) or 8 (BN=64)
         constexpr int kRowsPerIter = 32 / kLanesPerRow;
-        constexpr int kIters = 32 / kRowsPerIter;
-        constexpr int kRB = 16;
-        const int sub = lane / kLanesPerRow, col = (lane % kLanesPerRow) * 4;
-        float* stg = staging + (size_t)q * 32 * kLd;
+        constexpr int kIters = 32 / kRowsPerIter;        // 16 or 8 row-steps cover the warp's 32 rows: one residual batch
+        const int sub = lane / kLanesPerRow, col = hf * kCols + (lane % kLanesPerRow) * 4;
+        float* stg = staging + (size_t)((hf * 4 + q) * 32) * kLd;
         uint32_t ti = 0;
         for (int id = blockIdx.x; id < total; id += gridDim.x, ++ti) {
             int b, oy0, ox0, n0;
             tile_coords(id, b, oy0, ox0, n0);
             const uint32_t set = ti & 1, use = ti >> 1;
-            float4 res[kRB];
-            auto row_offset = [&](int it, bool& ok) -> size_t {
+            float4 res[kIters];
+            // offsets relative to the tile's first pixel fit 32 bits (8 rows x Wo x Cout); validity of the 16 row-steps as a bit mask
+            const size_t tile_base = (((size_t)b * args.Ho + oy0) * args.Wo + ox0) * args.Cout + n0 + col;
+            auto rel_offset = [&](int it, bool& ok) -> uint32_t {
                 const int row = q * 32 + it * kRowsPerIter + sub;
-                const int oy = oy0 + row / kTcTW, ox = ox0 + row % kTcTW;
-                ok = oy < args.Ho && ox < args.Wo;
-                return (((size_t)b * args.Ho + oy) * args.Wo + ox) * args.Cout + n0 + col;
+                const int ry = row / kTcTW, rx = row % kTcTW;
+                ok = oy0 + ry < args.Ho && ox0 + rx < args.Wo;
+                return (uint32_t)(ry * args.Wo + rx) * (uint32_t)args.Cout;
             };
-            auto prefetch = [&](int base) {
+            const float* res_base = args.residual ? args.residual + tile_base : nullptr;
+            float* out_base = args.out + tile_base;
+            uint32_t okmask = 0;
 #pragma unroll
-                for (int i = 0; i < kRB; ++i) {
-                    bool ok;
-                    const size_t off = row_offset(base + i, ok);
-                    res[i] = (ok && args.residual) ? __ldg(reinterpret_cast<const float4*>(args.residual + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            };
-            prefetch(0);
+            for (int i = 0; i < kIters; ++i) {
+                bool ok;
+                const uint32_t off = rel_offset(i, ok);
+                okmask |= (ok ? 1u : 0u) << i;
+                res[i] = (ok && res_base) ? __ldg(reinterpret_cast<const float4*>(res_base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
             if (args.bias) bi = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + col));
 
             mbar_wait(&tmem_full[set], use & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int cc = 0; cc < BN / 32; ++cc) {
-                uint32_t v[32], u[32];
-                const uint32_t taddr = tmem_base + set * (2u * BN) + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
-                tc_ld32(taddr, v);
-                tc_ld32(taddr + BN, u);
+            for (int cc = 0; cc < kCols / 16; ++cc) {
+                uint32_t v[16], u[16];
+                const uint32_t taddr = tmem_base + set * (2u * BN) + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * kCols + cc * 16);
+                tc_ld16(taddr, v);
+                tc_ld16(taddr + BN, u);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
+                for (int j = 0; j < 16; j += 4) {
                     float4 o;
                     o.x = __uint_as_float(v[j]) + __uint_as_float(u[j]);
                     o.y = __uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1]);
                     o.z = __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]);
                     o.w = __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3]);
-                    *reinterpret_cast<float4*>(stg + lane * kLd + cc * 32 + j) = o;
+                    *reinterpret_cast<float4*>(stg + lane * kLd + cc * 16 + j) = o;
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[set]);   // accumulator set free for the tile after next
-#pragma unroll 1
-            for (int base = 0; base < kIters; base += kRB) {
-                if (base > 0) prefetch(base);
 #pragma unroll
-                for (int i = 0; i < kRB; ++i) {
+            for (int i = 0; i < kIters; ++i) {
+                if ((okmask >> i) & 1u) {
                     bool ok;
-                    const size_t off = row_offset(base + i, ok);
-                    if (ok) {
-                        float4 o = *reinterpret_cast<const float4*>(stg + ((base + i) * kRowsPerIter + sub) * kLd + col);
-                        o.x += bi.x + res[i].x; o.y += bi.y + res[i].y; o.z += bi.z + res[i].z; o.w += bi.w + res[i].w;
-                        if (args.relu) {
-                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                        }
-                        *reinterpret_cast<float4*>(args.out + off) = o;
+                    const uint32_t off = rel_offset(i, ok);
+                    float4 o = *reinterpret_cast<const float4*>(stg + (i * kRowsPerIter + sub) * kLd + (lane % kLanesPerRow) * 4);
+                    o.x += bi.x + res[i].x; o.y += bi.y + res[i].y; o.z += bi.z + res[i].z; o.w += bi.w + res[i].w;
+                    if (args.relu) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                     }
+                    *reinterpret_cast<float4*>(out_base + off) = o;
                 }
             }
             __syncwarp();   // staging rows are rewritten by the next tile's phase 1
