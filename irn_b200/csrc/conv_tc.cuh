@@ -706,75 +706,75 @@ conv_tc_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&split[s]);
         }
-        if (warp < 6) {
-        // ---- epilogue on warps 2-5 (same as conv_tc_kernel: TMEM -> shared staging -> coalesced stores, residual rows prefetched)
-        constexpr int kLd = BN + 4;
-        constexpr int kRB = 16;
-        const int col = lane * 4;
-        float* stg = reinterpret_cast<float*>(smem) + (size_t)q * 32 * kLd;
-        float4 res[kRB];
-        auto row_offset = [&](int it, bool& ok) -> size_t {
-            const int rr = q * 32 + it;
-            const int oy = oy0 + rr / kTcTW, ox = ox0 + rr % kTcTW;
-            ok = oy < args.Ho && ox < args.Wo;
-            return (((size_t)b * args.Ho + oy) * args.Wo + ox) * args.Cout + n0 + col;
+        {
+        // ---- epilogue on all eight split warps: TMEM lane quarter q, channel half `half` (64 of the 128 channels each), so a
+        // warp's whole 32-row slice of the residual is in flight in one batch before the accumulator is ready
+        constexpr int kCols = BN / 2;
+        constexpr int kLd = kCols + 4;
+        constexpr int kIters = 16;                       // 2 rows per step (16 lanes x float4 per row)
+        const int sub = lane >> 4, col = half * kCols + (lane & 15) * 4;
+        float* stg = reinterpret_cast<float*>(smem) + (size_t)((half * 4 + q) * 32) * kLd;
+        const size_t tile_base = (((size_t)b * args.Ho + oy0) * args.Wo + ox0) * args.Cout + n0 + col;
+        auto rel_offset = [&](int it, bool& ok) -> uint32_t {
+            const int rr = q * 32 + it * 2 + sub;
+            const int ry = rr / kTcTW, rx = rr % kTcTW;
+            ok = oy0 + ry < args.Ho && ox0 + rx < args.Wo;
+            return (uint32_t)(ry * args.Wo + rx) * (uint32_t)args.Cout;
         };
-        auto prefetch = [&](int base) {
+        const float* res_base = args.residual ? args.residual + tile_base : nullptr;
+        float* out_base = args.out + tile_base;
+        float4 res[kIters];
+        uint32_t okmask = 0;
 #pragma unroll
-            for (int i = 0; i < kRB; ++i) {
-                bool ok;
-                const size_t off = row_offset(base + i, ok);
-                res[i] = (ok && args.residual) ? __ldg(reinterpret_cast<const float4*>(args.residual + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        };
-        prefetch(0);
+        for (int i = 0; i < kIters; ++i) {
+            bool ok;
+            const uint32_t off = rel_offset(i, ok);
+            okmask |= (ok ? 1u : 0u) << i;
+            res[i] = (ok && res_base) ? __ldg(reinterpret_cast<const float4*>(res_base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
         if (args.bias) bi = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + col));
         mbar_wait(acc_full, 0);
         tc_fence_after();
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc) {
-            uint32_t v[32], u[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32);
-            tc_ld32(taddr, v);
-            tc_ld32(taddr + 2u * BN, u);
+        for (int cc = 0; cc < kCols / 16; ++cc) {
+            uint32_t v[16], u[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * kCols + cc * 16);
+            tc_ld16(taddr, v);
+            tc_ld16(taddr + 2u * BN, u);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (KB >= 2) {
-                uint32_t t2[32];
-                tc_ld32(taddr + (uint32_t)BN, t2);
+                uint32_t t2[16];
+                tc_ld16(taddr + (uint32_t)BN, t2);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t2[j]));
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t2[j]));
             }
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < 16; j += 4) {
                 float4 o;
                 o.x = __uint_as_float(v[j]) + __uint_as_float(u[j]);
                 o.y = __uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1]);
                 o.z = __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]);
                 o.w = __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3]);
-                *reinterpret_cast<float4*>(stg + lane * kLd + cc * 32 + j) = o;
+                *reinterpret_cast<float4*>(stg + lane * kLd + cc * 16 + j) = o;
             }
         }
         __syncwarp();
-#pragma unroll 1
-        for (int base = 0; base < 32; base += kRB) {
-            if (base > 0) prefetch(base);
 #pragma unroll
-            for (int i = 0; i < kRB; ++i) {
+        for (int i = 0; i < kIters; ++i) {
+            if ((okmask >> i) & 1u) {
                 bool ok;
-                const size_t off = row_offset(base + i, ok);
-                if (ok) {
-                    float4 o = *reinterpret_cast<const float4*>(stg + (base + i) * kLd + col);
-                    o.x += bi.x + res[i].x; o.y += bi.y + res[i].y; o.z += bi.z + res[i].z; o.w += bi.w + res[i].w;
-                    if (args.relu) {
-                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                    }
-                    *reinterpret_cast<float4*>(args.out + off) = o;
+                const uint32_t off = rel_offset(i, ok);
+                float4 o = *reinterpret_cast<const float4*>(stg + (i * 2 + sub) * kLd + (lane & 15) * 4);
+                o.x += bi.x + res[i].x; o.y += bi.y + res[i].y; o.z += bi.z + res[i].z; o.w += bi.w + res[i].w;
+                if (args.relu) {
+                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                 }
+                *reinterpret_cast<float4*>(out_base + off) = o;
             }
         }
-        }   // warp < 6
+        }
     }
     tc_fence_before();
     __syncthreads();
