@@ -160,9 +160,13 @@ def run_reference(a, rank):
     sample = "1 image/step: PIL 4-scale preprocessing + 4-scale CAM (torch CPU fp32) + EdgeDisplacement + dense 256-step walk " \
              "(setup + 8 x one measured fp32 squaring of the 16384^2 transition matrix, flush-denormal on) + labels; stage seconds %s" % \
              {k: round(v, 3) for k, v in parts.items()}
+    cfg = config(a.batch, a.gpus)      # the workload of the CUDA arm; every step here walks a bounded sample of it
+    cfg["inputs"] = "decoded uint8 images; pyramids built by PIL on the host, as the reference's loader does"
+    cfg["l2"] = "n/a (host run)"
+    cfg["sample"] = "1 image of the batch per step"
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warm,
                       "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                      "data": "synthetic", "config": config(1, 1),
+                      "data": "synthetic", "config": cfg,
                       "cpu_baseline": {"value": val, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": sample},
                       "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
