@@ -135,7 +135,7 @@ def cpu_baseline_and_parity(out, ids, labels):
     return cpu, parity
 
 
-def run_reference(a, rank):
+def run_reference(a, rank, out_stream):
     """CPU oracle port of the reference path, one image per step (bounded sample), all host threads."""
     import torch
     if rank != 0:
@@ -164,11 +164,12 @@ def run_reference(a, rank):
     cfg["inputs"] = "decoded uint8 images; pyramids built by PIL on the host, as the reference's loader does"
     cfg["l2"] = "n/a (host run)"
     cfg["sample"] = "1 image of the batch per step"
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warm,
+    out_stream.write(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warm,
                       "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                       "data": "synthetic", "config": cfg,
                       "cpu_baseline": {"value": val, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": sample},
-                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}) + "\n")
+    out_stream.flush()
 
 
 def clocks_mhz(clocks):
@@ -178,13 +179,24 @@ def clocks_mhz(clocks):
         return 1800.0
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner there when NCCL_DEBUG is set)
+    write to file descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON line goes to
+    a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def main():
     a = parse()
+    out_stream = _claim_stdout()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if a.impl == "reference":
-        run_reference(a, rank)
+        run_reference(a, rank, out_stream)
         return
 
     import torch
@@ -342,7 +354,8 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"], line["parity"] = cpu_baseline_and_parity(out, ids, labels)
     if rank == 0:
-        print(json.dumps(line))
+        out_stream.write(json.dumps(line) + "\n")
+        out_stream.flush()
     if world > 1:
         dist.destroy_process_group()
 
