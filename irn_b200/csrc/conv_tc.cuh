@@ -784,6 +784,246 @@ conv_tc_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent kernel with the A operand in tensor memory, for the 64-channel layers with short reductions (layer1's 3x3 and
+// 256->64, the stem): the persistent tile loop / double-buffered accumulators / 8-warp epilogue of conv_tc_persist_kernel with
+// the split of conv_tc_ts_kernel.  Why: with N = 64 an SS-mode MMA reads 6 KB of operands from shared memory per 32 cycles of
+// tensor time (192 B/clk against the 128 B/clk the SM has) and the hi/lo split adds 48 KB per k-block: layer1's 3x3 ran at
+// 1255 cycles per k-block = the shared-memory bound (152 KB).  With A in TMEM a k-block moves 72 KB through shared memory (TMA
+// 32 + split reads 16 + B operand reads 24), and the smaller stages (32 KB) allow a five-deep ring = 80 KB of activations in
+// flight per SM for the memory-bound 256->64 reductions.
+//   TMEM columns: [0,256) two accumulator sets x (main 64 | cross 64); [256,384) two A slots x (hi 32 | lo 32)
+//   warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 split (thread = tile row), warps 6-13 epilogue
+constexpr int kPtsBN = 64;
+constexpr int kPtsStages = 5;
+constexpr int kPtsStageBytes = 16384 + 2 * kPtsBN * 128;          // A raw | B_hi | B_lo
+constexpr int kPtsLd = kPtsBN / 2 + 4;
+constexpr int kPtsStagingBytes = 2 * 128 * kPtsLd * 4;
+constexpr size_t kPtsSmem = 1024 + (size_t)kPtsStages * kPtsStageBytes + kPtsStagingBytes + 256;
+
+__global__ void __launch_bounds__(kTcPersistThreads, 1)
+conv_tc_persist_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
+    constexpr int BN = kPtsBN;
+    constexpr int S = kPtsStages;
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    unsigned char* smem = tc_smem_raw;
+    float* staging = reinterpret_cast<float*>(smem + S * kPtsStageBytes);
+    uint64_t* bars = (uint64_t*)(smem + S * kPtsStageBytes + kPtsStagingBytes);
+    uint64_t* full = bars;                     // [S] TMA landed
+    uint64_t* split = bars + S;                // [S] A_hi / A_lo of the k-block are in TMEM
+    uint64_t* empty = bars + 2 * S;            // [S] MMAs finished reading the stage
+    uint64_t* a_free = bars + 3 * S;           // [2] MMAs finished reading TMEM A slot
+    uint64_t* tmem_full = bars + 3 * S + 2;    // [2] MMA -> epilogue
+    uint64_t* tmem_empty = bars + 3 * S + 4;   // [2] epilogue -> MMA
+    uint32_t* tmem_slot = (uint32_t*)(bars + 3 * S + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = args.Cout / BN;
+    const int m_tiles = args.tiles_x * args.tiles_y * args.B;
+    const int total = m_tiles * n_tiles;
+    const int cblocks = args.Cin / kTcBK;
+    const int KB = args.mode == 1 ? args.ksize : args.ksize * args.ksize * cblocks;
+
+    if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) __trap();
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&split[s], 4);
+            mbar_init(&empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_free[i], 1);
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 8);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t kAcol = 256;
+
+    auto tile_coords = [&](int id, int& b, int& oy0, int& ox0, int& n0) {
+        const int m = id / n_tiles;
+        n0 = (id % n_tiles) * BN;
+        ox0 = (m % args.tiles_x) * kTcTW;
+        oy0 = ((m / args.tiles_x) % args.tiles_y) * kTcTH;
+        b = m / (args.tiles_x * args.tiles_y);
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&maps.a);
+            tma_prefetch_desc(&maps.b_hi);
+            tma_prefetch_desc(&maps.b_lo);
+            uint32_t g = 0;
+            for (int id = blockIdx.x; id < total; id += gridDim.x) {
+                int b, oy0, ox0, n0;
+                tile_coords(id, b, oy0, ox0, n0);
+                for (int kb = 0; kb < KB; ++kb, ++g) {
+                    const uint32_t s = g % S, it = g / S;
+                    mbar_wait(&empty[s], (it & 1) ^ 1);
+                    unsigned char* st = smem + s * kPtsStageBytes;
+                    const int tap = kb / cblocks, cb = kb % cblocks;
+                    const int r = tap / args.ksize, ss = tap % args.ksize;
+                    mbar_arrive_expect_tx(&full[s], 16384u + 2u * BN * 128u);
+                    if (args.mode == 1)
+                        tma_load_4d(st, &maps.a, &full[s], 0, ox0, oy0 * 2 + kb, b);
+                    else
+                        tma_load_4d(st, &maps.a, &full[s], cb * kTcBK, ox0 * args.stride - args.pad + ss, oy0 * args.stride - args.pad + r, b);
+                    tma_load_2d(st + 16384, &maps.b_hi, &full[s], kb * kTcBK, n0);
+                    tma_load_2d(st + 16384 + BN * 128, &maps.b_lo, &full[s], kb * kTcBK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc(128, BN);
+            uint32_t g = 0, ti = 0;
+            for (int id = blockIdx.x; id < total; id += gridDim.x, ++ti) {
+                const uint32_t set = ti & 1, use = ti >> 1;
+                mbar_wait(&tmem_empty[set], (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + set * (2u * BN);
+                for (int kb = 0; kb < KB; ++kb, ++g) {
+                    const uint32_t s = g % S, it = g / S, slot = g & 1;
+                    mbar_wait(&full[s], it & 1);       // B tiles landed
+                    mbar_wait(&split[s], it & 1);      // A_hi / A_lo in TMEM slot
+                    tc_fence_after();
+                    const uint32_t b_hi = smem_u32(smem + s * kPtsStageBytes + 16384), b_lo = b_hi + BN * 128;
+                    const uint32_t a_t = tmem_base + kAcol + slot * 64u;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const uint64_t db_hi = tc_smem_desc(b_hi + k4 * 32), db_lo = tc_smem_desc(b_lo + k4 * 32);
+                        const uint32_t ta_hi = a_t + k4 * 8, ta_lo = a_t + 32 + k4 * 8;
+                        tc_mma_tf32_ts(acc, ta_hi, db_hi, idesc, (kb | k4) != 0);
+                        tc_mma_tf32_ts(acc + BN, ta_lo, db_hi, idesc, (kb | k4) != 0);
+                        tc_mma_tf32_ts(acc + BN, ta_hi, db_lo, idesc, 1);
+                    }
+                    tc_commit(&empty[s]);
+                    tc_commit(&a_free[slot]);
+                }
+                tc_commit(&tmem_full[set]);
+            }
+        }
+    } else if (warp < 6) {
+        // ---- split warps: thread = tile row = TMEM lane; the row's 128-byte slice of the swizzled TMA tile -> hi / lo -> TMEM
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        uint32_t g = 0;
+        for (int id = blockIdx.x; id < total; id += gridDim.x) {
+            for (int kb = 0; kb < KB; ++kb, ++g) {
+                const uint32_t s = g % S, it = g / S, slot = g & 1;
+                mbar_wait(&full[s], it & 1);
+                const float4* arow = reinterpret_cast<const float4*>(smem + s * kPtsStageBytes + row * 128);
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 v = arow[c ^ (row & 7)];      // SWIZZLE_128B: 16-byte chunk c of row r lives at chunk c ^ (r % 8)
+                    const float h0 = tf32_hi(v.x), h1 = tf32_hi(v.y), h2 = tf32_hi(v.z), h3 = tf32_hi(v.w);
+                    hi[4 * c] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1); hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
+                    lo[4 * c] = __float_as_uint(v.x - h0); lo[4 * c + 1] = __float_as_uint(v.y - h1);
+                    lo[4 * c + 2] = __float_as_uint(v.z - h2); lo[4 * c + 3] = __float_as_uint(v.w - h3);
+                }
+                mbar_wait(&a_free[slot], ((g >> 1) & 1) ^ 1);   // the MMAs of k-block g-2 released this TMEM slot
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + kAcol + slot * 64u;
+                tc_st32(taddr, hi);
+                tc_st32(taddr + 32, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split[s]);
+            }
+        }
+    } else {
+        // ---- epilogue warps 6..13 (as in conv_tc_persist_kernel): TMEM lane quarter = warp % 4, channel half = (warp - 6) / 4
+        const int q = warp & 3;
+        const int hf = (warp - 6) >> 2;
+        constexpr int kCols = BN / 2;
+        constexpr int kLd = kPtsLd;
+        constexpr int kLanesPerRow = kCols / 4;          // 8
+        constexpr int kRowsPerIter = 32 / kLanesPerRow;  // 4
+        constexpr int kIters = 32 / kRowsPerIter;        // 8
+        const int sub = lane / kLanesPerRow, col = hf * kCols + (lane % kLanesPerRow) * 4;
+        float* stg = staging + (size_t)((hf * 4 + q) * 32) * kLd;
+        uint32_t ti = 0;
+        for (int id = blockIdx.x; id < total; id += gridDim.x, ++ti) {
+            int b, oy0, ox0, n0;
+            tile_coords(id, b, oy0, ox0, n0);
+            const uint32_t set = ti & 1, use = ti >> 1;
+            float4 res[kIters];
+            const size_t tile_base = (((size_t)b * args.Ho + oy0) * args.Wo + ox0) * args.Cout + n0 + col;
+            auto rel_offset = [&](int it, bool& ok) -> uint32_t {
+                const int rr = q * 32 + it * kRowsPerIter + sub;
+                const int ry = rr / kTcTW, rx = rr % kTcTW;
+                ok = oy0 + ry < args.Ho && ox0 + rx < args.Wo;
+                return (uint32_t)(ry * args.Wo + rx) * (uint32_t)args.Cout;
+            };
+            const float* res_base = args.residual ? args.residual + tile_base : nullptr;
+            float* out_base = args.out + tile_base;
+            uint32_t okmask = 0;
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) {
+                bool ok;
+                const uint32_t off = rel_offset(i, ok);
+                okmask |= (ok ? 1u : 0u) << i;
+                res[i] = (ok && res_base) ? __ldg(reinterpret_cast<const float4*>(res_base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (args.bias) bi = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + col));
+
+            mbar_wait(&tmem_full[set], use & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < kCols / 16; ++cc) {
+                uint32_t v[16], u[16];
+                const uint32_t taddr = tmem_base + set * (2u * BN) + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * kCols + cc * 16);
+                tc_ld16(taddr, v);
+                tc_ld16(taddr + BN, u);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 o;
+                    o.x = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                    o.y = __uint_as_float(v[j + 1]) + __uint_as_float(u[j + 1]);
+                    o.z = __uint_as_float(v[j + 2]) + __uint_as_float(u[j + 2]);
+                    o.w = __uint_as_float(v[j + 3]) + __uint_as_float(u[j + 3]);
+                    *reinterpret_cast<float4*>(stg + lane * kLd + cc * 16 + j) = o;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[set]);
+#pragma unroll
+            for (int i = 0; i < kIters; ++i) {
+                if ((okmask >> i) & 1u) {
+                    bool ok;
+                    const uint32_t off = rel_offset(i, ok);
+                    float4 o = *reinterpret_cast<const float4*>(stg + (i * kRowsPerIter + sub) * kLd + (lane % kLanesPerRow) * 4);
+                    o.x += bi.x + res[i].x; o.y += bi.y + res[i].y; o.z += bi.z + res[i].z; o.w += bi.w + res[i].w;
+                    if (args.relu) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    }
+                    *reinterpret_cast<float4*>(out_base + off) = o;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
 // ---- 2-CTA cluster helpers (weight tile multicast)
 __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;

@@ -252,6 +252,20 @@ static int launch_tc(const Conv& c, const float* in, int B, int H, int W, int Ho
 }
 
 // Tensor-core stem: x4 = zero-haloed NHWC4 input [B, Hin+6, Win+8, 4]; out NHWC [B,Ho,Wo,64] with bias + ReLU.
+// A-from-TMEM persistent kernel for the 64-channel layers (IRN_TC_PERSIST_TS=0 selects the shared-memory-operand one for A/B runs)
+static bool persist_ts_enabled() {
+    static const int v = getenv("IRN_TC_PERSIST_TS") ? atoi(getenv("IRN_TC_PERSIST_TS")) : 1;
+    return v != 0;
+}
+static int persist_ts_attr() {
+    static bool set = false;
+    if (!set) {
+        IRN_CUDA(cudaFuncSetAttribute(conv_tc_persist_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPtsSmem));
+        set = true;
+    }
+    return kOk;
+}
+
 static int launch_tc_stem(const Conv& c, const float* x4, int B, int Hin, int Win, float* out, cudaStream_t st) {
     static bool attr_set = false;
     static int n_sm = 0;
@@ -282,6 +296,13 @@ static int launch_tc_stem(const Conv& c, const float* x4, int B, int Hin, int Wi
     a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
     a.mode = 1;
     const long long total = (long long)a.tiles_x * a.tiles_y * B;
+    if (persist_ts_enabled()) {
+        int rc2 = persist_ts_attr();
+        if (rc2) return rc2;
+        conv_tc_persist_ts_kernel<<<(unsigned)(total < n_sm ? total : n_sm), kTcPersistThreads, kPtsSmem, st>>>(maps, a);
+        IRN_LAUNCH_CHECK("conv_tc_persist_ts_kernel(stem)");
+        return kOk;
+    }
     conv_tc_persist_kernel<64><<<(unsigned)(total < n_sm ? total : n_sm), kTcPersistThreads, TcPersistCfg<64>::kSmem, st>>>(maps, a);
     IRN_LAUNCH_CHECK("conv_tc_persist_kernel(stem)");
     return kOk;
@@ -317,6 +338,12 @@ static int launch_tc_persist(const Conv& c, const float* in, int B, int H, int W
     a.mode = 0;
     const long long total = (long long)a.tiles_x * a.tiles_y * B * (c.cout / BN);
     const unsigned grid = (unsigned)(total < n_sm ? total : n_sm);
+    if (BN == 64 && persist_ts_enabled()) {
+        if ((rc = persist_ts_attr())) return rc;
+        conv_tc_persist_ts_kernel<<<grid, kTcPersistThreads, kPtsSmem, st>>>(maps, a);
+        IRN_LAUNCH_CHECK("conv_tc_persist_ts_kernel");
+        return kOk;
+    }
     conv_tc_persist_kernel<BN><<<grid, kTcPersistThreads, TcPersistCfg<BN>::kSmem, st>>>(maps, a);
     IRN_LAUNCH_CHECK("conv_tc_persist_kernel");
     return kOk;

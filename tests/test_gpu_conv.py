@@ -12,6 +12,9 @@ pytestmark = pytest.mark.gpu
 CASES = [  # cin, cout, k, stride, pad, B, H, W
     (64, 256, 1, 1, 0, 2, 40, 48),
     (64, 64, 3, 1, 1, 2, 37, 53),      # ragged tiles
+    (64, 64, 3, 1, 1, 4, 128, 160),    # 640 tiles: several per persistent CTA (both accumulator sets, ring wrap-around)
+    (256, 64, 1, 1, 0, 4, 96, 128),    # 8 k-blocks per tile through the 5-stage ring, A operand from TMEM
+    (64, 256, 1, 1, 0, 4, 96, 128),    # 768 tiles through the shared-memory-operand persistent kernel
     (128, 128, 3, 2, 1, 2, 64, 64),
     (256, 512, 1, 2, 0, 2, 33, 47),
     (512, 128, 1, 1, 0, 3, 16, 16),
