@@ -41,7 +41,7 @@ FLAGS = [
 ]
 PASSES = ["train_cam", "make_cam", "eval_cam", "cam_to_ir_label", "train_irn", "make_ins_seg", "eval_ins_seg", "make_sem_seg", "eval_sem_seg"]
 HOT_STEPS = {"make_cam": "make_cam", "make_ins_seg": "make_ins_seg_labels", "make_sem_seg": "make_sem_seg_labels"}   # pass -> module
-EVAL_STEPS = {"eval_cam": "eval_cam", "eval_sem_seg": "eval_sem_seg"}   # host-side evaluators (need VOC ground truth)
+EVAL_STEPS = {"eval_cam": "eval_cam", "eval_sem_seg": "eval_sem_seg", "eval_ins_seg": "eval_ins_seg"}   # host-side evaluators (need VOC ground truth)
 
 
 def parse(argv=None):

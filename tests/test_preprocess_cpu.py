@@ -54,3 +54,11 @@ def test_abi_coefficients_equal_oracle(n_in, n_out):
 def test_abi_lut_equals_oracle():
     assert np.array_equal(preprocess.normalize_lut(), R.normalize_lut())
     assert preprocess.rescaled_size(375, 500, 0.5) == R.rescaled_size(375, 500, 0.5) == (188, 250)
+
+
+def test_oracle_resize_equals_recorded_pillow():
+    """The committed outputs of Pillow 12.2.0 (tests/golden/make_resize_golden.py): the pin that travels with the repo."""
+    from conftest import golden_path
+    g = np.load(golden_path("resize_pillow.npz"))
+    for i, (H, W, oh, ow) in enumerate(g["cases"]):
+        assert np.array_equal(R.pil_bicubic_resize_u8(g["img%d" % i], int(oh), int(ow)), g["out%d" % i])
