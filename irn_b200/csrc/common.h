@@ -36,4 +36,18 @@ inline int check_cuda(cudaError_t e, const char* what) {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// cudaFuncSetAttribute and the SM count belong to the CURRENT device: launch helpers keep one flag / value per device so that a
+// process driving several GPUs (one host thread each) configures every one of them.
+struct DeviceOnce {
+    bool done[64] = {};
+    int n_sm[64] = {};
+    // slot of the current device (a device index beyond the table shares slot 63 and is simply configured again on every call)
+    int slot() const {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return dev >= 0 && dev < 63 ? dev : 63;
+    }
+    bool need(int s) const { return s == 63 || !done[s]; }
+};
+
 }  // namespace irn

@@ -224,10 +224,11 @@ static inline int conv_out(int n, int k, int s, int p) { return (n + 2 * p - k) 
 template <int BN, int STAGES, int NACC>
 static int launch_tc(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
                      cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce once;
+    const int ds = once.slot();
+    if (once.need(ds)) {
         IRN_CUDA(cudaFuncSetAttribute((conv_tc_kernel<BN, STAGES, NACC>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(BN, STAGES)));
-        attr_set = true;
+        once.done[ds] = true;
     }
     TcMaps maps;
     maps.b_hi = BN == 64 && c.bn == 128 ? c.map_bhi64 : c.map_bhi;
@@ -258,24 +259,26 @@ static bool persist_ts_enabled() {
     return v != 0;
 }
 static int persist_ts_attr() {
-    static bool set = false;
-    if (!set) {
+    static DeviceOnce once;
+    const int ds = once.slot();
+    if (once.need(ds)) {
         IRN_CUDA(cudaFuncSetAttribute(conv_tc_persist_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPtsSmem));
-        set = true;
+        once.done[ds] = true;
     }
     return kOk;
 }
 
 static int launch_tc_stem(const Conv& c, const float* x4, int B, int Hin, int Win, float* out, cudaStream_t st) {
-    static bool attr_set = false;
-    static int n_sm = 0;
-    if (!attr_set) {
+    static DeviceOnce once;
+    const int ds = once.slot();
+    if (once.need(ds)) {
         IRN_CUDA(cudaFuncSetAttribute(conv_tc_persist_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcPersistCfg<64>::kSmem));
         int dev = 0;
         IRN_CUDA(cudaGetDevice(&dev));
-        IRN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
+        IRN_CUDA(cudaDeviceGetAttribute(&once.n_sm[ds], cudaDevAttrMultiProcessorCount, dev));
+        once.done[ds] = true;
     }
+    const int n_sm = once.n_sm[ds];
     const int Hp = Hin + 6, Wp = Win + 8;
     const int Ho = conv_out(Hin, 7, 2, 3), Wo = conv_out(Win, 7, 2, 3);
     TcMaps maps;
@@ -311,15 +314,16 @@ static int launch_tc_stem(const Conv& c, const float* x4, int B, int Hin, int Wi
 template <int BN>
 static int launch_tc_persist(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out,
                              bool relu, cudaStream_t st) {
-    static bool attr_set = false;
-    static int n_sm = 0;
-    if (!attr_set) {
+    static DeviceOnce once;
+    const int ds = once.slot();
+    if (once.need(ds)) {
         IRN_CUDA(cudaFuncSetAttribute(conv_tc_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcPersistCfg<BN>::kSmem));
         int dev = 0;
         IRN_CUDA(cudaGetDevice(&dev));
-        IRN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
+        IRN_CUDA(cudaDeviceGetAttribute(&once.n_sm[ds], cudaDevAttrMultiProcessorCount, dev));
+        once.done[ds] = true;
     }
+    const int n_sm = once.n_sm[ds];
     TcMaps maps;
     maps.b_hi = BN == 64 && c.bn == 128 ? c.map_bhi64 : c.map_bhi;
     maps.b_lo = BN == 64 && c.bn == 128 ? c.map_blo64 : c.map_blo;
@@ -351,10 +355,11 @@ static int launch_tc_persist(const Conv& c, const float* in, int B, int H, int W
 
 static int launch_tc_ts(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
                         cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce once;
+    const int ds = once.slot();
+    if (once.need(ds)) {
         IRN_CUDA(cudaFuncSetAttribute(conv_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTsSmem));
-        attr_set = true;
+        once.done[ds] = true;
     }
     TcMaps maps;
     maps.b_hi = c.map_bhi;
@@ -374,10 +379,11 @@ static int launch_tc_ts(const Conv& c, const float* in, int B, int H, int W, int
     a.mode = 0;
     static const int use_pair = getenv("IRN_TC_PAIR") ? atoi(getenv("IRN_TC_PAIR")) : 0;   // measured: no gain (1322 vs 1323 us on the 3x3x512 layer), kept for A/B
     if (use_pair) {
-        static bool attr2 = false;
-        if (!attr2) {
+        static DeviceOnce once2;
+        const int ds2 = once2.slot();
+        if (once2.need(ds2)) {
             IRN_CUDA(cudaFuncSetAttribute(conv_tc_ts2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTsSmem));
-            attr2 = true;
+            once2.done[ds2] = true;
         }
         maps.b_hi = c.map_bhi64;    // each CTA of a pair loads 64 of the 128 weight rows and multicasts them
         maps.b_lo = c.map_blo64;

@@ -824,11 +824,12 @@ static int launch_fused(const RwWorkspace& ws, const float* x, const float* edge
     const int need = (h + kFR - 1) / kFR;
     int cs = 1;
     while (cs < need) cs *= 2;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce once;
+    const int ds = once.slot();
+    if (once.need(ds)) {
         IRN_CUDA(cudaFuncSetAttribute(rw_fused_kernel<PY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
         IRN_CUDA(cudaFuncSetAttribute(rw_fused_kernel<PY>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr_set = true;
+        once.done[ds] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)cs);
