@@ -3,12 +3,18 @@
 //   out[b,oy,ox,n] = act( sum_{r,s,c} in[b, oy*st-pad+r, ox*st-pad+s, c] * w[n,(r,s,c)] + bias[n] + residual )
 //
 // GEMM view per CTA: M = one 8x16 spatial tile of output pixels (128 rows), N = BN output channels,
-// K = taps x Cin walked in 32-channel slices.  Pipeline (warp-specialised, one CTA per SM):
-//   warp 0      TMA producer: 4-D box {32 ch, 16 px, 8 rows, 1 image} of the input per tap (zero fill outside the
-//               image = zero padding; element strides give stride-2 convs), 2-D boxes of the pre-split weights
-//   warps 2-5   split the fp32 activation tile in place into A_hi = round_tf32(a), A_lo = a - A_hi
-//   warp 1      one thread issues tcgen05.mma kind::tf32:  D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  (fp32 in TMEM)
-//   warps 2-5   epilogue: tcgen05.ld, + bias, + residual, ReLU, float4 stores
+// K = taps x Cin walked in 32-channel slices.  All kernels are warp-specialised (one CTA per SM):
+//   TMA producer  4-D box {32 ch, 16 px, 8 rows, 1 image} of the input per tap (zero fill outside the image = zero
+//                 padding; element strides give stride-2 convs), 2-D boxes of the host-split weights (hi / lo planes)
+//   split warps   A_hi = round_tf32(a), A_lo = a - A_hi of the activation tile, into shared memory or into TMEM
+//   MMA issuer    one thread: tcgen05.mma kind::tf32,  D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  (fp32 accumulators in TMEM)
+//   epilogue      tcgen05.ld -> shared staging -> coalesced + bias, + residual, ReLU float4 stores
+// Four kernels share these pieces (dispatch: nets.cu, run_conv):
+//   conv_tc_kernel             one tile per CTA, operands from shared memory (the first version; classifier conv today)
+//   conv_tc_persist_kernel     persistent tile loop, two accumulator sets, 8 epilogue warps: K <= 640, 128-channel N tiles
+//   conv_tc_persist_ts_kernel  the same with the A operand in TMEM: the 64-channel layers and the stem
+//   conv_tc_ts_kernel          one tile per CTA, A operand in TMEM, three accumulators: K > 640
+// (conv_tc_ts2_kernel: CTA-pair weight multicast experiment, off by default: no gain.)
 // Why 3xTF32: plain TF32 misses the 1e-4 CAM parity bar by 20x; the split keeps ~21 mantissa bits.
 #pragma once
 #include <cuda.h>
