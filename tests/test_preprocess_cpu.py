@@ -62,3 +62,26 @@ def test_oracle_resize_equals_recorded_pillow():
     g = np.load(golden_path("resize_pillow.npz"))
     for i, (H, W, oh, ow) in enumerate(g["cases"]):
         assert np.array_equal(R.pil_bicubic_resize_u8(g["img%d" % i], int(oh), int(ow)), g["out%d" % i])
+
+
+def test_rescaled_size_matches_imutils_rounding():
+    """misc/imutils.py:19-22 rounds half to even (np.round); the device path must request the same sizes."""
+    from irn_b200.misc import imutils
+    for H, W in [(375, 500), (333, 500), (281, 500), (500, 375), (3, 5), (512, 512)]:
+        img = np.zeros((H, W, 3), np.uint8)
+        for s in (0.5, 1.5, 2.0, 0.75, 1.25):
+            assert imutils.pil_rescale(img, s, 3).shape[:2] == preprocess.rescaled_size(H, W, s)
+
+
+def test_abi_resize_argument_errors():
+    from irn_b200 import _lib
+    L = _lib.lib()
+    assert L.irn_resize_ksize(0, 4) == 0 and L.irn_resize_ksize(4, 0) == 0
+    assert L.irn_resize_ksize(512, 256) == 9 and L.irn_resize_ksize(512, 1024) == 5     # support 2*scale (down) / 2 (up), both sides + centre
+    b = np.zeros((4, 2), np.int32)
+    k = np.zeros((4, 9), np.int32)
+    assert L.irn_resize_coeffs(0, 4, b.ctypes.data, k.ctypes.data) != 0
+    assert L.irn_resize_coeffs(8, 4, None, k.ctypes.data) != 0
+    assert b"irn_resize_coeffs" in L.irn_last_error()
+    assert L.irn_normalize_lut(None, None, None) != 0
+    assert L.irn_resize_workspace_bytes(None, 1) == 0
