@@ -1,4 +1,5 @@
-"""How fast is the CPU oracle's conv path on this host at different torch thread counts? (development aid)"""
+"""How fast is the CPU oracle's conv path on this host at different torch thread counts?  (Probe behind bench.py's choice of
+32 threads for the cpu_baseline leg; lives under tests/ because it imports the oracle.  Run: python tests/probe_cpu_threads.py)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
