@@ -1,5 +1,4 @@
 """Instance path (P1-P4) host wrappers over the C ABI: step/make_ins_seg_labels.py:18-105."""
-import ctypes
 
 import numpy as np
 import torch

@@ -1,6 +1,5 @@
 """Host-side checks that need no GPU: the C-ABI library loads, exports every symbol the header
 declares, and its host-only entry points (PathIndex) are integer bit-exact."""
-import ctypes
 import hashlib
 import json
 import os

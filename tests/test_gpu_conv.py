@@ -1,6 +1,5 @@
 """The convolution kernels (SIMT fp32 and tcgen05 3xTF32) against a plain torch fp32 reference of the same
 op (F.conv2d + batch_norm on the GPU with TF32 disabled)."""
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F

@@ -1,7 +1,6 @@
 """N>1 host logic on CPU: the reference's stride partition (misc/torchutils.py:66-68) and the label-map gather,
 exercised with two gloo ranks."""
 import os
-import sys
 
 import numpy as np
 import torch

@@ -1,7 +1,7 @@
 """Does a pinned H2D copy on a side stream overlap with kernels launched through libirn_b200 on torch's current stream?"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from irn_b200.ops import Conv2d
 dev = torch.device("cuda:0")
 x_host = torch.empty((256, 1024, 1024), dtype=torch.float32).pin_memory()   # 1 GiB
