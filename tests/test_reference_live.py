@@ -1,0 +1,59 @@
+"""Build-container only: re-run the UNMODIFIED reference (/root/reference through oracle/refshim.py) on a few small seeded
+inputs and compare with the committed fixtures, so the goldens are demonstrably what the reference produces -- not a stale
+copy.  Skipped wherever /root/reference does not exist (e.g. the GPU box)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import golden_path
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree only exists in the build container")
+
+SCRIPT = r"""
+import hashlib, json, os, sys
+import numpy as np, torch
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, "tests", "golden"))
+from oracle import refshim
+import make_golden as mg
+from irn_b200 import synth
+refshim.install()
+os.chdir(refshim.REF)
+from misc import indexing as ref_indexing
+out = {}
+pi = ref_indexing.PathIndex(5, (21, 26))
+out["path_sha"] = mg.sha_path_index(pi)
+h, w, r = 12, 17, 5
+edge = synth.edge_map(h, w, "uniform", 7)
+pi = ref_indexing.PathIndex(r, (h + r, w + 2 * r))
+ep = torch.nn.functional.pad(torch.from_numpy(edge), (r, r, 0, r), value=1.0)
+out["aff_sha"] = hashlib.sha256(np.ascontiguousarray(ref_indexing.edge_to_affinity(ep[None], pi.path_indices).numpy()).tobytes()).hexdigest()
+name, hh, ww, C, et, kind, seed = mg.RW_CASES[1]
+with torch.no_grad():
+    rw = ref_indexing.propagate_to_edge(torch.from_numpy(synth.seeds(C, hh, ww, seed)), torch.from_numpy(synth.edge_map(hh, ww, kind, seed)),
+                                        radius=5, beta=10, exp_times=et).numpy().astype(np.float32)
+out["rw_name"] = name
+out["rw"] = rw.reshape(-1).tolist()
+print("RESULT" + json.dumps(out))
+"""
+
+
+def test_fixtures_are_live_reference_outputs():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", SCRIPT % {"root": root}], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    out = json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT")][0][6:])
+    gold = json.load(open(golden_path("path_index.json")))
+    assert out["path_sha"] == gold["r5_21x26"]["sha256"]
+    import hashlib
+    g = np.load(golden_path("affinity_12x17.npz"))
+    assert out["aff_sha"] == hashlib.sha256(np.ascontiguousarray(g["aff"]).tobytes()).hexdigest()
+    g = np.load(golden_path("rw_%s.npz" % out["rw_name"]))
+    live = np.asarray(out["rw"], np.float32).reshape(g["rw"].shape)
+    # same code, same seeds, same machine class: the matrix products may differ in the last bits between BLAS builds / thread counts
+    assert np.abs(live - g["rw"]).max() < 1e-6
