@@ -1,0 +1,73 @@
+"""Host-side loader logic of the steps (C1 data path), on the CPU: item formats of the datasets in both modes, the
+batch-size-1 collation the steps rely on, the stride partition of the shards, run_sample's flag table."""
+import os
+import types
+
+import numpy as np
+import torch
+from PIL import Image
+
+from irn_b200.misc import torchutils
+from irn_b200.step import _common
+from irn_b200.voc12 import dataloader as dl
+from irn_b200 import synth
+
+
+def _voc_tree(tmp_path, sizes):
+    root = tmp_path / "voc"
+    os.makedirs(root / "JPEGImages")
+    ids, labels = [], {}
+    for i, (H, W) in enumerate(sizes):
+        name = "2007_%06d" % (32 + i)
+        Image.fromarray(synth.image(i, H, W)).save(root / "JPEGImages" / (name + ".jpg"), format="PNG")   # lossless pixels
+        ids.append(name)
+        labels[int(name.replace("_", ""))] = synth.label(i)
+    (root / "list.txt").write_text("\n".join(ids) + "\n")
+    dl._cls_labels["voc12/cls_labels.npy"] = labels
+    return root, ids
+
+
+def test_msf_dataset_item_formats(tmp_path):
+    sizes = [(37, 50), (40, 33)]
+    root, ids = _voc_tree(tmp_path, sizes)
+    scales = (1.0, 0.5, 1.5)
+    full = dl.VOC12ClassificationDatasetMSF(str(root / "list.txt"), str(root), scales=scales)
+    dec = dl.VOC12ClassificationDatasetMSF(str(root / "list.txt"), str(root), scales=scales, decode_only=True)
+    assert len(full) == len(dec) == 2
+    for i, (H, W) in enumerate(sizes):
+        a, b = full[i], dec[i]
+        assert a["name"] == b["name"] == ids[i] and a["size"] == b["size"] == (H, W)
+        assert torch.equal(a["label"], b["label"]) and a["label"].shape == (20,)
+        assert "img_u8" not in a and "img" not in b
+        assert b["img_u8"].dtype == np.uint8 and b["img_u8"].shape == (H, W, 3) and b["img_u8"].flags.writeable
+        assert np.array_equal(b["img_u8"], synth.image(i, H, W))
+        assert [x.shape for x in a["img"]] == [(2, 3, H, W), (2, 3, round(H * 0.5), round(W * 0.5)), (2, 3, round(H * 1.5), round(W * 1.5))]
+        assert np.array_equal(a["img"][0][1], a["img"][0][0][..., ::-1])          # second entry = W-flip (voc12/dataloader.py:199)
+    one = dl.VOC12ClassificationDatasetMSF(str(root / "list.txt"), str(root), scales=(1.0,))[0]["img"]
+    assert isinstance(one, np.ndarray) and one.shape == (2, 3, 37, 50)            # single scale: no list (voc12/dataloader.py:200-201)
+
+
+def test_collate_one_and_shards(tmp_path):
+    ds = dl.SyntheticMSF(5, size=(32, 48), scales=(1.0, 0.5), decode_only=True)
+    pack = _common.collate_one([ds[3]])
+    assert pack["size"] == (32, 48) and all(isinstance(v, int) for v in pack["size"])
+    assert pack["img_u8"].shape == (1, 32, 48, 3) and pack["img_u8"].dtype == torch.uint8
+    assert pack["label"].shape == (1, 20) and pack["name"] == ["2007_000003"]
+    shards = torchutils.split_dataset(ds, 2)
+    assert [len(s) for s in shards] == [3, 2]
+    assert [s[0]["name"] for s in shards] == ["2007_000000", "2007_000001"]     # rank r takes r, r+n, ... (misc/torchutils.py:66-68)
+    assert getattr(getattr(shards[0], "dataset", shards[0]), "scales") == (1.0, 0.5)   # what work_loop hands to attach_pyramid
+    args = types.SimpleNamespace(synthetic=4, voc12_root="")
+    assert _common.device_pyramid(args) is True
+    assert _common.make_dataset(args, "/nonexistent/list.txt", (1.0,)).decode_only is True
+    args.device_pyramid = False
+    assert _common.make_dataset(args, "/nonexistent/list.txt", (1.0,)).decode_only is False
+    assert _common.attach_pyramid({"img": "kept"}, (1.0,)) == {"img": "kept"}     # host-pyramid items pass through untouched
+
+
+def test_run_sample_flag_table():
+    import run_sample
+    names = [f[0] for f in run_sample.FLAGS]
+    assert len(names) == len(set(names)) and {"device_pyramid", "synthetic", "cam_scales", "beta", "exp_times"} <= set(names)
+    assert run_sample._bool("False") is False and run_sample._bool("true") is True
+    assert run_sample._scales("1.0,0.5") == (1.0, 0.5)
