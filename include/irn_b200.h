@@ -189,6 +189,8 @@ int irn_cam_merge(const float* const* cams, const int* hs, const int* ws, int n_
  * irn_instance_seeds      P3 separte_score_by_mask (:77-80): out[k*I+i] = cams[k] * (instance_map == i).
  * irn_segment_stats       P4 detect_instance (:82-105) statistics: per segment label l: area[l], max_bits[l] =
  *                         float bits of max(scores[index-1]) over the segment; arrays int32 [H*W+1].
+ * irn_segment_masks       P4 detect_instance: the `pred_mask` planes (:96-101) -- masks[m] = (labels == seg_ids[m]) as
+ *                         0/1 bytes (numpy bool layout) [M,H,W]; seg_ids device int32 [M].
  */
 int irn_find_centroids(const float* dp, int32_t* centroids, int h, int w, int iterations, irn_stream_t stream);
 int irn_connected_components(const int32_t* values, int32_t* labels, int h, int w, void* scratch, irn_stream_t stream);
@@ -199,6 +201,8 @@ int irn_instance_seeds(const float* cams, const int32_t* instance_map, int K, in
                        irn_stream_t stream);
 int irn_segment_stats(const int32_t* labels, const int32_t* index, const float* scores, int H, int W,
                       int32_t* area, int32_t* max_bits, irn_stream_t stream);
+int irn_segment_masks(const int32_t* labels, const int32_t* seg_ids, int M, int H, int W, uint8_t* masks,
+                      irn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * C1  multi-scale input preparation on the device.  Replaces, for a decoded uint8 image, the per-scale body of

@@ -162,9 +162,42 @@ __global__ void segment_stats_kernel(const int32_t* __restrict__ labels, const i
     atomicMax(&max_bits[l], __float_as_int(scores[(size_t)(index[p] - 1) * n + p]));   // scores >= 0
 }
 
+// Detection masks: out[m][p] = (labels[p] == seg_ids[m]) as bytes (numpy bool), 16 pixels per thread.
+__global__ void segment_masks_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ seg_ids, uint8_t* __restrict__ out, int M,
+                                     int n) {
+    const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (p0 >= n) return;
+    const int m = blockIdx.y;
+    const int id = seg_ids[m];
+    uint8_t v[16];
+    const bool full = p0 + 16 <= n;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (full || p0 + i < n) ? (labels[p0 + i] == id ? 1 : 0) : 0;
+    uint8_t* o = out + (size_t)m * n + p0;
+    if (full && (((size_t)m * n + p0) & 15) == 0) {
+        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(v);
+    } else {
+        for (int i = 0; i < 16 && p0 + i < n; ++i) o[i] = v[i];
+    }
+}
+
 }  // namespace irn
 
 using namespace irn;
+
+// masks uint8 [M,H,W] (0/1) of the M segments whose labels are listed in seg_ids (device int32 [M])
+extern "C" int irn_segment_masks(const int32_t* labels, const int32_t* seg_ids, int M, int H, int W, uint8_t* masks, irn_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    launch_counter() = 0;
+    if (M < 0 || H <= 0 || W <= 0) return fail(kBadArg, "irn_segment_masks: bad size");
+    if (M == 0) return kOk;
+    if (!labels || !seg_ids || !masks) return fail(kBadArg, "irn_segment_masks: null pointer");
+    if (M > 65535) return fail(kUnsupported, "irn_segment_masks: more than 65535 segments");
+    const int n = H * W;
+    segment_masks_kernel<<<dim3((unsigned)((n + 16 * 256 - 1) / (16 * 256)), (unsigned)M), 256, 0, st>>>(labels, seg_ids, masks, M, n);
+    IRN_LAUNCH_CHECK("segment_masks_kernel");
+    return kOk;
+}
 
 extern "C" int irn_find_centroids(const float* dp, int32_t* centroids, int h, int w, int iterations, irn_stream_t stream_) {
     cudaStream_t st = (cudaStream_t)stream_;

@@ -699,7 +699,7 @@ static size_t irn_head_floats(int B, const TrunkShapes& s) {
     n += g2 * 448;                 // dp1|dp2|dp_up3 concat
     n += g2 * 256;                 // dp7 activations
     n += g2 * 3;                   // edge logits + dp
-    n += (size_t)B * 16 * 4 + 64;  // GN sums (fp64)
+    n += (size_t)B * 16 * 4 + 64;  // GN sums (fp64): B x (<= 16 groups, enforced in run_head) x (sum, sum of squares)
     return n + 64 * 16;
 }
 
@@ -714,7 +714,7 @@ static int run_head(const irn_net* net, const Head& hd, const float* x, int B, i
                     int coff, cudaStream_t st) {
     int rc = run_conv(net, hd.conv, x, B, H, W, nullptr, raw, false, st, nullptr, nullptr);
     if (rc) return rc;
-    if (hd.conv.cout > 256 || 256 % hd.conv.cout != 0 || hd.groups > 32) return fail(kUnsupported, "GroupNorm head with %d channels / %d groups", hd.conv.cout, hd.groups);
+    if (hd.conv.cout > 256 || 256 % hd.conv.cout != 0 || hd.groups > 16) return fail(kUnsupported, "GroupNorm head with %d channels / %d groups", hd.conv.cout, hd.groups);
     IRN_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * hd.groups * 2 * sizeof(double), st));
     {
         const int slices = std::max(1, std::min(256, (H * W) / 256));

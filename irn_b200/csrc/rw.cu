@@ -81,6 +81,9 @@ static int upload_tables(int radius, cudaStream_t stream, int* n_dst_out) {
         h.py[j] = (signed char)t.points[j].first;
         h.px[j] = (signed char)t.points[j].second;
     }
+    // Kernels launched earlier on ANY stream may still be reading the previous radius' table: a radius change is rare
+    // (the hot path only uses 5), so wait for the whole device before overwriting the symbol.
+    IRN_CUDA(cudaDeviceSynchronize());
     IRN_CUDA(cudaMemcpyToSymbolAsync(c_tab, &h, sizeof(h), 0, cudaMemcpyHostToDevice, stream));
     IRN_CUDA(cudaStreamSynchronize(stream));   // `h` is reused; happens once per (device, radius)
     if (dev < 64) {

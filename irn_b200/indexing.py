@@ -126,7 +126,7 @@ def propagate_to_edge(x, edge, radius=5, beta=10, exp_times=8):
     return rw.view(-1, 1, h, w)
 
 
-def rw_labels(rw, keys, size, bg_thres=0.25, want_index=False, want_scores=False):
+def rw_labels(rw, keys, size, bg_thres=0.25, want_index=False, want_scores=False, out=None):
     """step/make_sem_seg_labels.py:37,43-49.  rw cuda fp32 [C,1,h,w] or [C,h,w]; keys: int
     sequence of 0-based class ids (len C) or None; size=(H,W).  Returns (labels uint8 [H,W]
     cuda, index int32 [H,W] | None, scores fp32 [C,H,W] | None)."""
@@ -137,7 +137,9 @@ def rw_labels(rw, keys, size, bg_thres=0.25, want_index=False, want_scores=False
     C = r.shape[0]
     H, W = int(size[0]), int(size[1])
     dev = r.device
-    labels = torch.empty((H, W), dtype=torch.uint8, device=dev)
+    if out is not None and (tuple(out.shape) != (H, W) or out.dtype != torch.uint8 or not out.is_contiguous() or out.device != dev):
+        raise _lib.IrnError("rw_labels: `out` must be a contiguous uint8 [H,W] tensor on the walk's device")
+    labels = out if out is not None else torch.empty((H, W), dtype=torch.uint8, device=dev)
     index = torch.empty((H, W), dtype=torch.int32, device=dev) if want_index else None
     scores = torch.empty((C, H, W), dtype=torch.float32, device=dev) if want_scores else None
     kh = None

@@ -63,26 +63,34 @@ def separate_score_by_mask(cams, instance_map, n_instances):
 def detect_instance(scores, index, class_ids, max_fragment_size=0):
     """step/make_ins_seg_labels.py:82-105.  scores cuda fp32 [C,H,W] (normalised upsampled walk), index cuda int32 [H,W]
     (argmax with background 0), class_ids: int sequence of length C.  Returns the reference's dict of numpy arrays
-    {'score' f32[M], 'mask' bool[M,H,W], 'class' int64[M]} ordered by (channel, raster order of the segment)."""
+    {'score' f32[M], 'mask' bool[M,H,W], 'class' int64[M]} ordered by (channel, raster order of the segment).
+    Components, per-segment area / max score and the mask planes are built on the device; the host only orders the
+    (few) segments."""
     _lib.require_cuda(scores, index)
     L = _lib.lib()
     C, H, W = scores.shape
+    dev = scores.device
+    index = index.contiguous()
     labels = connected_components(index)
-    area = torch.empty(H * W + 1, dtype=torch.int32, device=scores.device)
-    mx = torch.empty(H * W + 1, dtype=torch.int32, device=scores.device)
-    with torch.cuda.device(scores.device):
-        _lib.check(L.irn_segment_stats(_lib.ptr(labels), _lib.ptr(index.contiguous()), _lib.ptr(scores.contiguous()), H, W, _lib.ptr(area),
+    area = torch.empty(H * W + 1, dtype=torch.int32, device=dev)
+    mx = torch.empty(H * W + 1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.irn_segment_stats(_lib.ptr(labels), _lib.ptr(index), _lib.ptr(scores.contiguous()), H, W, _lib.ptr(area),
                                        _lib.ptr(mx), _lib.stream_ptr()), "irn_segment_stats")
-    lab = labels.cpu().numpy()
-    idx = index.cpu().numpy()
-    seg_ids = np.nonzero(area.cpu().numpy())[0]                     # ascending = raster order of first pixels
-    seg_area = area.cpu().numpy()[seg_ids]
-    seg_max = mx.cpu().numpy()[seg_ids].view(np.float32)
-    seg_chan = idx.reshape(-1)[seg_ids - 1] - 1                     # channel of the segment's first pixel
+    area_h = area.cpu().numpy()
+    seg_ids = np.nonzero(area_h)[0].astype(np.int32)                # ascending = raster order of first pixels
+    if seg_ids.size == 0:
+        return {"score": np.stack([], 0), "mask": None, "class": None}   # np.stack([]) raises like the reference
+    seg_area = area_h[seg_ids]
+    ids_dev = torch.from_numpy(seg_ids).to(dev)
+    seg_max = mx[ids_dev.long()].cpu().numpy().view(np.float32)
+    seg_chan = index.reshape(-1)[(ids_dev - 1).long()].cpu().numpy() - 1   # channel of the segment's first pixel
     order = np.lexsort((seg_ids, seg_chan))
-    score, mask, cls = [], [], []
-    for j in order:
-        score.append(np.float32(0) if seg_area[j] < max_fragment_size else seg_max[j])
-        mask.append(lab == seg_ids[j])
-        cls.append(np.asarray(class_ids)[seg_chan[j]])
-    return {"score": np.stack(score, 0), "mask": np.stack(mask, 0), "class": np.stack(cls, 0)}   # np.stack([]) raises like the reference
+    M = int(order.size)
+    masks = torch.empty((M, H, W), dtype=torch.uint8, device=dev)
+    ordered = torch.from_numpy(np.ascontiguousarray(seg_ids[order])).to(dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.irn_segment_masks(_lib.ptr(labels), _lib.ptr(ordered), M, H, W, _lib.ptr(masks), _lib.stream_ptr()), "irn_segment_masks")
+    score = np.where(seg_area[order] < max_fragment_size, np.float32(0), seg_max[order]).astype(np.float32)
+    cls = np.asarray(class_ids)[seg_chan[order]]
+    return {"score": score, "mask": masks.cpu().numpy().view(np.bool_), "class": cls}

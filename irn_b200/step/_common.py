@@ -3,11 +3,20 @@
 The reference repeats the same skeleton in step/make_cam.py, step/make_sem_seg_labels.py and
 step/make_ins_seg_labels.py: build the model class named on the command line, load its checkpoint, split the
 image list over the visible GPUs with the stride partition, spawn one worker per GPU, loop over a batch-size-1
-DataLoader.  Here that skeleton exists once; each step module only supplies its per-image function.
+DataLoader.  Here that skeleton exists once; each step module supplies its per-image function (the reference's loop
+body, one image at a time) and its per-batch function (the same arithmetic for a batch of equally-sized images through
+irn_b200.pipeline, used whenever the loader hands over decoded uint8 images: --device_pyramid, the default).
+
+Batched mode keeps the reference's observable behaviour: same files, same names, same formats; only the order in which
+files appear changes (images are bucketed by size, a bucket is flushed when it holds --step_batch images or at the end),
+and file writes overlap the GPU work of the next batch on a small thread pool.
 """
 import importlib
 import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
 
+import numpy as np
 import torch
 from torch.utils.data import DataLoader
 from torch.utils.data._utils.collate import default_collate
@@ -15,6 +24,8 @@ from torch.utils.data._utils.collate import default_collate
 from .. import preprocess
 from ..misc import torchutils
 from ..voc12 import dataloader as voc_data
+
+DEFAULT_STEP_BATCH = 16
 
 
 def collate_one(batch):
@@ -40,10 +51,19 @@ def device_pyramid(args):
     return bool(getattr(args, "device_pyramid", True))
 
 
+def step_batch(args):
+    """--step_batch N (default 16): images of equal size processed together; 1 = the reference's one-image loop."""
+    return max(1, int(getattr(args, "step_batch", DEFAULT_STEP_BATCH) or 1))
+
+
 def make_dataset(args, list_path, scales):
     """VOC images from --voc12_root, or seeded synthetic ones with --synthetic N."""
     if getattr(args, "synthetic", 0):
-        names = list_path if os.path.exists(list_path) else None
+        # one id list for ALL steps (the reference reads --train_list in make_cam but --infer_list in the label steps; with
+        # synthetic images the later steps must find the .npy files the first one wrote): --synthetic_list, else 2007_%06d
+        names = getattr(args, "synthetic_list", None) or None
+        if names is not None and not os.path.exists(names):
+            raise FileNotFoundError("--synthetic_list %s" % names)
         return voc_data.SyntheticMSF(int(args.synthetic), scales=scales, name_list=names, decode_only=device_pyramid(args))
     return voc_data.VOC12ClassificationDatasetMSF(list_path, voc12_root=args.voc12_root, scales=scales,
                                                   decode_only=device_pyramid(args))
@@ -59,18 +79,137 @@ def attach_pyramid(pack, scales):
     return pack
 
 
-def work_loop(process_id, model, dataset, args, per_image):
+class Writer:
+    """File output off the GPU-issuing thread.  A job is `fn(*args)` run on a pool thread after `event` (recorded on the
+    compute stream by the submitter) has completed; jobs do their device->host copies on a side stream of their own, so
+    they never queue behind the next batch's kernels.  At most `max_pending` jobs are in flight (bounds host and device
+    memory held by finished batches); exceptions surface in drain()."""
+
+    def __init__(self, device, threads=4, max_pending=8):
+        self.device = device
+        self.pool = ThreadPoolExecutor(max_workers=threads)
+        self.sem = threading.Semaphore(max_pending)
+        self.futures = []
+        self._tls = threading.local()
+
+    def stream(self):
+        s = getattr(self._tls, "stream", None)
+        if s is None:
+            s = torch.cuda.Stream(device=self.device)
+            self._tls.stream = s
+        return s
+
+    def to_host(self, tensors):
+        """Device tensors -> host tensors through this thread's side stream (call from inside a job)."""
+        s = self.stream()
+        with torch.cuda.stream(s):
+            out = [t.to("cpu", non_blocking=True) if t is not None else None for t in tensors]
+        s.synchronize()
+        return out
+
+    def submit(self, fn, *args):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.sem.acquire()
+
+        def job():
+            try:
+                with torch.cuda.device(self.device):
+                    ev.synchronize()
+                    fn(*args)
+            finally:
+                self.sem.release()
+        self.futures.append(self.pool.submit(job))
+        if len(self.futures) > 256:
+            self.futures = [f for f in self.futures if not (f.done() and f.exception() is None)]
+
+    def submit_host(self, fn, *args):
+        """A host-only job (no device event to wait for), same back-pressure and error collection."""
+        self.sem.acquire()
+
+        def job():
+            try:
+                fn(*args)
+            finally:
+                self.sem.release()
+        self.futures.append(self.pool.submit(job))
+
+    def map(self, fn, items):
+        return list(self.pool.map(fn, items))
+
+    def drain(self):
+        for f in self.futures:
+            f.result()
+        self.futures = []
+
+    def close(self):
+        self.drain()
+        self.pool.shutdown()
+
+
+class StepContext:
+    def __init__(self, model, args, device, scales):
+        from ..pipeline import PseudoLabelPipeline
+        self.model, self.args, self.device, self.scales = model, args, device, tuple(scales)
+        is_cam = hasattr(model, "classifier")
+        self.pipe = PseudoLabelPipeline(model if is_cam else None, None if is_cam else model, device, self.scales,
+                                        beta=float(getattr(args, "beta", 10)), exp_times=int(getattr(args, "exp_times", 8)))
+        self.writer = Writer(device)
+        self._pinned = {}
+
+    def stack_images(self, packs):
+        """The decoded images of a bucket as one device uint8 [N,H,W,3], staged through pinned host memory (two alternating
+        buffers per shape; a buffer is rewritten only after the upload that last read it has completed)."""
+        N = len(packs)
+        shape = (N,) + tuple(packs[0]["img_u8"].shape[1:])
+        if shape not in self._pinned and len(self._pinned) >= 8:      # VOC has hundreds of image sizes: bound the pinned pool
+            torch.cuda.current_stream(self.device).synchronize()
+            self._pinned.clear()
+        slot = self._pinned.setdefault(shape, {"bufs": [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(2)],
+                                               "done": [None, None], "i": 0})
+        k = slot["i"]
+        slot["i"] ^= 1
+        if slot["done"][k] is not None:
+            slot["done"][k].synchronize()
+        buf = slot["bufs"][k]
+        for i, p in enumerate(packs):
+            buf[i].copy_(p["img_u8"][0])
+        dev = buf.to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        slot["done"][k] = ev
+        return dev
+
+
+def work_loop(process_id, model, dataset, args, per_image, per_batch=None):
     """One GPU's share: the reference's `_work(process_id, model, dataset, args)` signature and loop order
-    (step/make_cam.py:16-59), with the per-image body supplied by the step."""
+    (step/make_cam.py:16-59), with the per-image / per-batch body supplied by the step."""
     shard = dataset[process_id]
-    n_gpus = torch.cuda.device_count()
-    loader = DataLoader(shard, shuffle=False, num_workers=args.num_workers // max(n_gpus, 1), pin_memory=False, collate_fn=collate_one)
+    n_gpus = max(torch.cuda.device_count(), 1)
+    loader = DataLoader(shard, shuffle=False, num_workers=args.num_workers // n_gpus, pin_memory=False, collate_fn=collate_one)
+    scales = getattr(getattr(shard, "dataset", shard), "scales", (1.0,))
+    bsz = step_batch(args)
     with torch.no_grad(), torch.cuda.device(process_id):
         model.cuda()
-        scales = getattr(getattr(shard, "dataset", shard), "scales", (1.0,))
-        for it, pack in enumerate(loader):
-            per_image(model, attach_pyramid(pack, scales), args)
-            progress(process_id, n_gpus, it, len(shard))
+        if per_batch is None or bsz == 1 or not device_pyramid(args):
+            for it, pack in enumerate(loader):
+                per_image(model, attach_pyramid(pack, scales), args)
+                progress(process_id, n_gpus, it, len(shard))
+            return
+        ctx = StepContext(model, args, torch.device("cuda", process_id), scales)
+        buckets = {}
+        try:
+            for it, pack in enumerate(loader):
+                key = (pack["size"], tuple(pack["img_u8"].shape))
+                b = buckets.setdefault(key, [])
+                b.append(pack)
+                if len(b) >= bsz:
+                    per_batch(ctx, buckets.pop(key))
+                progress(process_id, n_gpus, it, len(shard))
+            for packs in buckets.values():
+                per_batch(ctx, packs)
+        finally:
+            ctx.writer.close()
 
 
 def run_step(args, work, module_name, class_name, weights_path, strict, list_path, scales, opening="[ "):
@@ -90,3 +229,8 @@ def run_step(args, work, module_name, class_name, weights_path, strict, list_pat
         torch.multiprocessing.spawn(work, nprocs=n_gpus, args=(model, shards, args), join=True)
     print("]")
     torch.cuda.empty_cache()
+
+
+def load_cam_dicts(ctx, names, cam_out_dir):
+    """The stored CAMs of make_cam for a batch (np.load(...).item(), step/make_sem_seg_labels.py:34): read on the pool."""
+    return ctx.writer.map(lambda n: np.load(os.path.join(cam_out_dir, n + ".npy"), allow_pickle=True).item(), names)

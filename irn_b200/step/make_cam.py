@@ -4,6 +4,7 @@ a pickled ``{"keys": LongTensor[K], "cam": FloatTensor[K,h/4,w/4], "high_res": n
 import os
 
 import numpy as np
+import torch
 
 from .. import cam_ops
 from . import _common
@@ -17,8 +18,29 @@ def cam_one_image(model, pack, args):
             {"keys": keys, "cam": strided.cpu(), "high_res": highres.cpu().numpy()})
 
 
+def _save(ctx, names, keys, strided, highres, out_dir):
+    """Pool thread: one device->host copy per tensor kind for the whole batch, then one np.save per image."""
+    counts = [int(k.size) for k in keys]
+    lo, hi = ctx.writer.to_host([torch.cat(strided, 0), torch.cat(highres, 0)])
+    o = 0
+    for name, k, c in zip(names, keys, counts):
+        np.save(os.path.join(out_dir, name + ".npy"),
+                {"keys": torch.from_numpy(k.astype(np.int64)), "cam": lo[o:o + c].clone(), "high_res": hi[o:o + c].numpy().copy()})
+        o += c
+
+
+def cam_batch(ctx, packs):
+    """The same body for a bucket of equally-sized decoded images (irn_b200.pipeline stages C1-C4)."""
+    args = ctx.args
+    x = ctx.stack_images(packs)
+    labels = torch.cat([p["label"] for p in packs], 0)
+    xs = ctx.pipe.pyramids(x, ctx.scales)
+    keys, strided, highres = ctx.pipe.cam_stage(xs, labels, packs[0]["size"], want_highres=True, scales=ctx.scales)
+    ctx.writer.submit(_save, ctx, [p["name"][0] for p in packs], keys, strided, highres, args.cam_out_dir)
+
+
 def _work(process_id, model, dataset, args):
-    _common.work_loop(process_id, model, dataset, args, cam_one_image)
+    _common.work_loop(process_id, model, dataset, args, cam_one_image, cam_batch)
 
 
 def run(args):

@@ -23,8 +23,26 @@ def ins_seg_one_image(model, pack, args):
     np.save(os.path.join(args.ins_seg_out_dir, name + ".npy"), detected)
 
 
+def ins_seg_batch(ctx, packs):
+    """step/make_ins_seg_labels.py:122-152 for a bucket of equally-sized images: one IRNet forward, one batched walk over
+    every (class, instance) channel of the bucket (irn_b200.pipeline.instance_stage)."""
+    args = ctx.args
+    names = [p["name"][0] for p in packs]
+    stored = _common.load_cam_dicts(ctx, names, args.cam_out_dir)
+    x = ctx.stack_images(packs)
+    x1 = ctx.pipe.pyramids(x, (1.0,))[0]
+    edges, dps = ctx.pipe.irn_stage(x1)
+    keys = [np.asarray(s["keys"]) for s in stored]
+    strided = [s["cam"].to(ctx.device, non_blocking=True) for s in stored]
+    dets = ctx.pipe.instance_stage(strided, keys, edges, dps, packs[0]["size"], float(args.ins_seg_bg_thres))
+    for name, det in zip(names, dets):
+        if det is None:     # the reference's np.stack([]) raises for an image without any detection
+            raise ValueError("need at least one array to stack (no instance detected in %s)" % name)
+        ctx.writer.submit_host(np.save, os.path.join(args.ins_seg_out_dir, name + ".npy"), det)
+
+
 def _work(process_id, model, dataset, args):
-    _common.work_loop(process_id, model, dataset, args, ins_seg_one_image)
+    _common.work_loop(process_id, model, dataset, args, ins_seg_one_image, ins_seg_batch)
 
 
 def run(args):

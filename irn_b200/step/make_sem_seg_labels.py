@@ -19,8 +19,30 @@ def sem_seg_one_image(model, pack, args):
     Image.fromarray(labels.cpu().numpy()).save(os.path.join(args.sem_seg_out_dir, name + ".png"))
 
 
+def _save(ctx, names, labels, out_dir):
+    (lab,) = ctx.writer.to_host([labels])
+    lab = lab.numpy()
+    for i, name in enumerate(names):
+        Image.fromarray(lab[i]).save(os.path.join(out_dir, name + ".png"))
+
+
+def sem_seg_batch(ctx, packs):
+    """step/make_sem_seg_labels.py:28-51 for a bucket of equally-sized images: one IRNet forward, one batched walk."""
+    args = ctx.args
+    names = [voc_data.decode_int_filename(p["name"][0]) for p in packs]
+    stored = _common.load_cam_dicts(ctx, names, args.cam_out_dir)
+    x = ctx.stack_images(packs)
+    x1 = ctx.pipe.pyramids(x, (1.0,))[0]
+    edges, _ = ctx.pipe.irn_stage(x1)
+    keys = [np.asarray(s["keys"]) for s in stored]
+    seeds = [s["cam"].to(ctx.device, non_blocking=True) for s in stored]
+    rw, counts = ctx.pipe.walk_stage(seeds, edges)
+    labels = ctx.pipe.label_stage(rw, counts, keys, packs[0]["size"], float(args.sem_seg_bg_thres))
+    ctx.writer.submit(_save, ctx, names, labels, args.sem_seg_out_dir)
+
+
 def _work(process_id, model, dataset, args):
-    _common.work_loop(process_id, model, dataset, args, sem_seg_one_image)
+    _common.work_loop(process_id, model, dataset, args, sem_seg_one_image, sem_seg_batch)
 
 
 def run(args):

@@ -99,9 +99,7 @@ class SyntheticMSF(Dataset):
     ids are taken from an image-name list when given, else 2007_000000 + index."""
 
     def __init__(self, n_items, size=(512, 512), scales=(1.0,), name_list=None, img_normal=TorchvisionNormalize(), decode_only=False):
-        from .. import synth
-        self.synth = synth
-        self.decode_only = decode_only
+        self.decode_only = decode_only       # (no module stored on the instance: shards are pickled for spawn / DataLoader workers)
         self.n, self.size, self.scales, self.img_normal = n_items, size, scales, img_normal
         self.names = None if name_list is None else load_img_name_list(name_list)[:n_items]
 
@@ -110,8 +108,9 @@ class SyntheticMSF(Dataset):
 
     def __getitem__(self, idx):
         name = decode_int_filename(self.names[idx]) if self.names is not None else "2007_%06d" % idx
-        img = self.synth.image(idx, *self.size)
-        out = {"name": name, "size": tuple(self.size), "label": torch.from_numpy(self.synth.label(idx))}
+        from .. import synth
+        img = synth.image(idx, *self.size)
+        out = {"name": name, "size": tuple(self.size), "label": torch.from_numpy(synth.label(idx))}
         if self.decode_only:
             out["img_u8"] = np.array(img)
         else:

@@ -124,6 +124,30 @@ def detect_instance(score_map, mask, class_id, max_fragment_size=0):
     return {"score": np.stack(sc, 0), "mask": np.stack(mk, 0), "class": np.stack(lb, 0)}
 
 
+def ins_seg_labels(cams, keys, edge, dp, size, beta=10, exp_times=8, bg_thres=0.25, walk=None):
+    """step/make_ins_seg_labels.py:131-150 for one image: centroids -> instance clusters -> per-instance seeds ->
+    walk -> x4 up, /max, bg plane, argmax -> one-hot -> detect_instance.  cams fp32 [K,h,w], keys int64 [K], edge [1,h,w],
+    dp [2,h,w] (numpy).  `walk(seeds[K*I,h,w], edge) -> [K*I,h,w]`; default = the exact fp64 stencil operator
+    (the reference's dense fp32 squaring is its own 3-7e-5 away from it)."""
+    from . import indexing as oi
+    dp = np.asarray(dp, np.float32)
+    cen = find_centroids(dp)
+    inst = cluster_centroids(cen, dp)                                           # bool [I,h,w]
+    seeds = np.asarray(cams, np.float32)[:, None] * inst[None].astype(np.float32)   # :77-80  [K,I,h,w]
+    K, I = seeds.shape[:2]
+    flat = seeds.reshape(K * I, *seeds.shape[2:])
+    if walk is None:
+        rw = oi.propagate_stencil(flat, np.asarray(edge, np.float32), 5, beta, 2 ** exp_times).astype(np.float32)
+    else:
+        rw = walk(flat, edge)
+    rw = torch.from_numpy(np.ascontiguousarray(rw, np.float32)).reshape(K * I, 1, *seeds.shape[2:])
+    up = upsample4_norm(rw, size)
+    bg = F.pad(up, (0, 0, 0, 0, 1, 0), value=bg_thres)
+    shape = one_hot(torch.argmax(bg, 0).numpy(), K * I + 1)[1:]
+    cls = np.repeat(np.asarray(keys), I)
+    return detect_instance(up.numpy(), shape, cls, max_fragment_size=size[0] * size[1] * 0.01)
+
+
 def split_indices(n_items, n_splits):
     # misc/torchutils.py:66-68
     return [np.arange(i, n_items, n_splits) for i in range(n_splits)]

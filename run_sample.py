@@ -7,7 +7,8 @@ so the reference's evaluation steps (step/eval_cam.py, step/eval_sem_seg.py, ste
 run here (make_cam, make_ins_seg_labels, make_sem_seg_labels); training / CRF / evaluation passes are the reference's own.
 
 Differences: --cam_network / --irn_network default to the B200 modules; flags the reference declares without a type
-(--beta, --exp_times, --*_bg_thres, --*_pass) are parsed; --synthetic N runs on N seeded synthetic images instead of VOC.
+(--beta, --exp_times, --*_bg_thres, --*_pass) are parsed; --synthetic N runs on N seeded synthetic images instead of VOC
+(--synthetic_list names them); --step_batch N images of equal size are processed together (1 = the reference's loop).
 """
 import argparse
 import os
@@ -25,7 +26,8 @@ def _scales(v):
 
 # (flag, default, type) in the reference's order: environment, dataset, CAM, relation mining, IRNet, random walk, outputs
 FLAGS = [
-    ("num_workers", os.cpu_count() // 2, int), ("voc12_root", "", str), ("synthetic", 0, int), ("device_pyramid", True, _bool),
+    ("num_workers", os.cpu_count() // 2, int), ("voc12_root", "", str), ("synthetic", 0, int), ("synthetic_list", "", str), ("device_pyramid", True, _bool),
+    ("step_batch", 16, int),
     ("train_list", "voc12/train_aug.txt", str), ("val_list", "voc12/val.txt", str), ("infer_list", "voc12/train.txt", str),
     ("chainer_eval_set", "train", str),
     ("cam_network", "irn_b200.cam", str), ("cam_crop_size", 512, int), ("cam_batch_size", 16, int), ("cam_num_epoches", 5, int),

@@ -120,6 +120,18 @@ def gen_nets():
     return cam, irn
 
 
+def load_nets():
+    import net.resnet50_cam as rcam
+    import net.resnet50_irn as rirn
+    cam = rcam.CAM()
+    cam.load_state_dict(synth.cam_state_dict(), strict=True)
+    cam.eval()
+    irn = rirn.EdgeDisplacement()
+    irn.load_state_dict(synth.irn_state_dict(), strict=False)
+    irn.eval()
+    return cam, irn
+
+
 def gen_steps(cam, irn):
     """Drive the reference's own step._work loops over a tiny synthetic VOC tree."""
     from PIL import Image
@@ -195,6 +207,99 @@ def gen_steps(cam, irn):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def gen_steps512(cam, irn):
+    """The benchmark's size: ONE 512x512 synthetic image through the reference's own three `_work` loops (4-scale CAM at
+    256/512/768/1024 inputs, EdgeDisplacement, the dense 16384^2 walk squared 8 times -- minutes of CPU sgemm -- for the
+    sem-seg AND the ins-seg step).  Forward hooks / a wrapper around propagate_to_edge record the intermediate tensors
+    (per-scale CAMs, edge, dp, walk outputs) without touching the reference's code.  The image is stored losslessly
+    (PNG bytes under the .jpg name: PIL sniffs the format) so tests regenerate it from the seed."""
+    from PIL import Image
+    import voc12.dataloader as vd
+    import step.make_cam
+    import step.make_sem_seg_labels
+    import step.make_ins_seg_labels
+    from misc import indexing as ref_indexing
+
+    def safe_list(path):
+        return np.array([int(l.strip().replace("_", "")) for l in open(path) if l.strip()], dtype=np.int64)
+    vd.load_img_name_list = safe_list
+    from torch.utils.data import DataLoader as _DL
+    from torch.utils.data._utils.collate import default_collate
+
+    def _collate(batch):
+        out = default_collate(batch)
+        out["size"] = (int(batch[0]["size"][0]), int(batch[0]["size"][1]))
+        return out
+
+    def _loader(ds, **kw):
+        return _DL(ds, collate_fn=_collate, **kw)
+    for m in (step.make_cam, step.make_sem_seg_labels, step.make_ins_seg_labels):
+        m.DataLoader = _loader
+
+    name, seed = "2007_000170", 512      # a train_aug id whose real label has two classes
+    label = vd.cls_labels_dict[int(name.replace("_", ""))]
+    assert label.sum() >= 2, label
+    tmp = tempfile.mkdtemp(prefix="irn_golden512_")
+    rec = {"cam_scales": [], "walks": [], "irn": []}
+    h1 = cam.register_forward_hook(lambda m, i, o: rec["cam_scales"].append((tuple(i[0].shape), o.detach().numpy().copy())))
+    h2 = irn.register_forward_hook(lambda m, i, o: rec["irn"].append((o[0].detach().numpy().copy(), o[1].detach().numpy().copy())))
+    orig = ref_indexing.propagate_to_edge
+
+    def spy(x, edge, **kw):
+        out = orig(x, edge, **kw)
+        rec["walks"].append((tuple(x.shape), out.detach().numpy().copy()))
+        return out
+    ref_indexing.propagate_to_edge = spy
+    try:
+        os.makedirs(os.path.join(tmp, "JPEGImages"))
+        Image.fromarray(synth.image(seed, 512, 512)).save(os.path.join(tmp, "JPEGImages", name + ".jpg"), format="PNG")
+        lst = os.path.join(tmp, "list.txt")
+        open(lst, "w").write(name + "\n")
+        args = types.SimpleNamespace(num_workers=0, cam_out_dir=os.path.join(tmp, "cam"), sem_seg_out_dir=os.path.join(tmp, "sem"),
+                                     ins_seg_out_dir=os.path.join(tmp, "ins"), beta=10, exp_times=8,
+                                     sem_seg_bg_thres=0.25, ins_seg_bg_thres=0.25)
+        for d in (args.cam_out_dir, args.sem_seg_out_dir, args.ins_seg_out_dir):
+            os.makedirs(d)
+        ds = vd.VOC12ClassificationDatasetMSF(lst, voc12_root=tmp, scales=(1.0, 0.5, 1.5, 2.0))
+        with torch.no_grad():
+            step.make_cam._work(1, cam, [None, ds], args)
+        ds1 = vd.VOC12ClassificationDatasetMSF(lst, voc12_root=tmp, scales=(1.0,))
+        import time
+        with torch.no_grad():
+            t0 = time.time()
+            step.make_sem_seg_labels._work(1, irn, [None, ds1], args)
+            print("sem-seg loop %.0f s" % (time.time() - t0), flush=True)
+            t0 = time.time()
+            step.make_ins_seg_labels._work(1, irn, [None, ds1], args)
+            print("ins-seg loop %.0f s" % (time.time() - t0), flush=True)
+        out = {"name": np.array(name), "seed": np.array(seed), "label": label}
+        for shp, y in rec["cam_scales"]:
+            out["camscale_%d" % shp[-1]] = y            # keyed by the input width: 512, 256, 768, 1024
+        cd = np.load(os.path.join(args.cam_out_dir, name + ".npy"), allow_pickle=True).item()
+        out["cam_keys"] = cd["keys"].numpy()
+        out["cam_cam"] = cd["cam"].numpy()
+        out["cam_high_s4"] = np.ascontiguousarray(cd["high_res"][:, 1::4, 2::4])     # every 4th pixel (rows 1::4, cols 2::4) of the full-res maps
+        out["cam_high_max"] = cd["high_res"].reshape(cd["high_res"].shape[0], -1).max(1)
+        out["edge"], out["dp"] = rec["irn"][0]
+        assert np.array_equal(rec["irn"][0][0], rec["irn"][1][0])
+        out["walk_sem"] = rec["walks"][0][1]
+        out["walk_ins"] = rec["walks"][1][1]
+        out["walk_ins_in_shape"] = np.asarray(rec["walks"][1][0])
+        out["sem"] = np.asarray(Image.open(os.path.join(args.sem_seg_out_dir, name + ".png")))
+        ins = np.load(os.path.join(args.ins_seg_out_dir, name + ".npy"), allow_pickle=True).item()
+        out["ins_score"] = np.asarray(ins["score"], np.float32)
+        out["ins_mask"] = np.packbits(ins["mask"].astype(bool), axis=-1)
+        out["ins_mask_shape"] = np.asarray(ins["mask"].shape)
+        out["ins_class"] = np.asarray(ins["class"])
+        print("steps512", name, {k: getattr(v, "shape", None) for k, v in out.items()})
+        np.savez_compressed(os.path.join(HERE, "steps512.npz"), **out)
+    finally:
+        h1.remove()
+        h2.remove()
+        ref_indexing.propagate_to_edge = orig
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def gen_instance_fns():
     import step.make_ins_seg_labels as rins
     out = {}
@@ -238,6 +343,8 @@ def main():
         cam, irn = gen_nets()
         if want("steps"):
             gen_steps(cam, irn)
+    if only is not None and "steps512" in only:      # minutes of CPU: only on request
+        gen_steps512(*load_nets())
 
 
 if __name__ == "__main__":

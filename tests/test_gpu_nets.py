@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_path
+from conftest import golden_path, record
 from irn_b200 import synth
 from irn_b200.cam import CAM
 from irn_b200.irn import EdgeDisplacement
@@ -36,7 +36,9 @@ def test_cam_forward_vs_reference(cuda_dev, cam_model):
         ref = g["y%d" % i]
         assert y.shape == ref.shape
         scale = ref.max()
-        assert np.abs(y - ref).max() / scale < 1e-4, "normalised CAM err %g" % (np.abs(y - ref).max() / scale)
+        err = np.abs(y - ref).max() / scale
+        record("cam_forward_vs_reference", input=list(g["x%d" % i].shape[-2:]), normalised_err=err)
+        assert err < 1e-4, "normalised CAM err %g" % err
 
 
 def test_cam_batch_equals_single(cuda_dev, cam_model):
@@ -60,8 +62,13 @@ def test_edge_displacement_vs_reference(cuda_dev, irn_model):
             x = np.stack([x, x[..., ::-1].copy()])
         e, d = irn_model(torch.from_numpy(x).to(cuda_dev))
         assert e.shape == g["edge%d" % i].shape and d.shape == g["dp%d" % i].shape
-        assert np.abs(e.cpu().numpy() - g["edge%d" % i]).max() < 1e-4
-        assert np.abs(d.cpu().numpy() - g["dp%d" % i]).max() < 1e-3    # dp is in pixels (|dp| up to ~3): 1e-3 abs ~ 3e-4 relative
+        e_err = np.abs(e.cpu().numpy() - g["edge%d" % i]).max()
+        d_err = np.abs(d.cpu().numpy() - g["dp%d" % i]).max()
+        d_max = np.abs(g["dp%d" % i]).max()
+        record("edge_displacement_vs_reference", input=list(x.shape[-2:]), edge_err=e_err, dp_err=d_err, dp_absmax=d_max)
+        assert e_err < 1e-4                               # edge is a sigmoid output in (0,1): absolute = relative to full scale
+        # dp is an unbounded displacement in stride-4 pixels: the 1e-4 contract is held relative to the field's own range
+        assert d_err < 1e-4 * max(1.0, d_max), "dp err %g with |dp|max %g" % (d_err, d_max)
 
 
 def test_state_dict_keys_match_reference_format(cam_model, irn_model):

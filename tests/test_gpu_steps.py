@@ -9,7 +9,7 @@ import pytest
 import torch
 from PIL import Image
 
-from conftest import golden_path
+from conftest import golden_path, check_detections, unpack_masks, record
 from irn_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -81,28 +81,115 @@ def test_make_sem_seg_labels_outputs(voc_tree):
         lab = np.asarray(Image.open(os.path.join(args.sem_seg_out_dir, name + ".png")))
         ref = g["sem%d" % i]
         assert lab.dtype == np.uint8 and lab.shape == ref.shape
-        assert (lab != ref).mean() < 5e-3, "label disagreement %g" % (lab != ref).mean()
+        dis = float((lab != ref).mean())
+        record("make_sem_seg_labels_vs_reference_png", image=name, disagreement=dis)
+        # the oracle's exact-operator walk itself sits 2e-3 from the reference's fp32 dense walk on these images
+        # (tests/test_oracle_golden.py); boundary pixels flip at 1e-5 float noise
+        assert dis < 2.5e-3, "label disagreement %g" % dis
 
 
 def test_make_ins_seg_labels_outputs(voc_tree):
+    """Against the dicts the reference's own loop saved: detection count and order, classes, scores (1e-4), masks."""
     g, ids, args = voc_tree
     from irn_b200.step import make_ins_seg_labels
     make_ins_seg_labels.run(args)
     for i, name in enumerate(ids):
         d = np.load(os.path.join(args.ins_seg_out_dir, name + ".npy"), allow_pickle=True).item()
-        shape = tuple(g["ins_mask_shape%d" % i])
-        ref_mask = np.unpackbits(g["ins_mask%d" % i], axis=-1, count=shape[-1]).astype(bool).reshape(shape)
+        ref_mask = unpack_masks(g, str(i))
         assert set(d) == {"score", "mask", "class"}
-        assert d["mask"].dtype == bool and d["mask"].shape[1:] == shape[1:]
-        # detections as a labelled image: identical up to boundary pixels
-        def paint(masks, classes):
-            out = np.zeros(shape[1:], np.int32)
-            for m, c in zip(masks, classes):
-                out[m] = int(c) + 1
-            return out
-        a, b = paint(d["mask"], d["class"]), paint(ref_mask, g["ins_class%d" % i])
-        assert (a != b).mean() < 1e-2
-        assert sorted(set(np.asarray(d["class"]).tolist())) == sorted(set(g["ins_class%d" % i].tolist()))
+        assert d["mask"].dtype == bool and d["mask"].shape[1:] == ref_mask.shape[1:]
+        worst = check_detections(d, g["ins_score%d" % i], ref_mask, g["ins_class%d" % i], score_tol=1e-4, pixel_tol=2.5e-3)
+        record("make_ins_seg_labels_vs_reference", image=name, detections=len(d["score"]), reference_detections=len(g["ins_score%d" % i]),
+               worst_mask_disagreement=worst, score_err=float(np.abs(np.sort(d["score"])[::-1][:3] - np.sort(g["ins_score%d" % i])[::-1][:3]).max()))
+
+
+def _copy_args(args, root, tag, **over):
+    a = types.SimpleNamespace(**vars(args))
+    for k in ("cam_out_dir", "sem_seg_out_dir", "ins_seg_out_dir"):
+        d = os.path.join(root, tag + "_" + k)
+        os.makedirs(d, exist_ok=True)
+        setattr(a, k, d)
+    for k, v in over.items():
+        setattr(a, k, v)
+    return a
+
+
+def _same_tree(a_dir, b_dir, names, kind):
+    for n in names:
+        if kind == "png":
+            assert np.array_equal(np.asarray(Image.open(os.path.join(a_dir, n + ".png"))), np.asarray(Image.open(os.path.join(b_dir, n + ".png")))), n
+            continue
+        a = np.load(os.path.join(a_dir, n + ".npy"), allow_pickle=True).item()
+        b = np.load(os.path.join(b_dir, n + ".npy"), allow_pickle=True).item()
+        assert set(a) == set(b)
+        for k in a:
+            x, y = (v.numpy() if isinstance(v, torch.Tensor) else np.asarray(v) for v in (a[k], b[k]))
+            assert type(a[k]) is type(b[k]) and x.dtype == y.dtype and np.array_equal(x, y), (n, k)
+
+
+def test_batched_steps_write_the_same_files(voc_tree, tmp_path):
+    """--step_batch 16 (buckets of equally-sized images through the batched pipeline, writer threads) against
+    --step_batch 1 (the reference's one-image loop): identical files, byte for byte, for all three steps.  Synthetic 64x96
+    images so that buckets really hold several images."""
+    _, _, args = voc_tree
+    from irn_b200.step import make_cam, make_sem_seg_labels, make_ins_seg_labels
+    from irn_b200.step import _common
+    names = ["2007_%06d" % i for i in range(5)]
+    real = _common.make_dataset
+
+    def small(a, list_path, scales):
+        from irn_b200.voc12 import dataloader
+        return dataloader.SyntheticMSF(5, size=(64, 96), scales=scales, decode_only=_common.device_pyramid(a))
+    _common.make_dataset = small
+    try:
+        one = _copy_args(args, str(tmp_path), "b1", synthetic=5, step_batch=1, exp_times=5)
+        many = _copy_args(args, str(tmp_path), "b16", synthetic=5, step_batch=3, exp_times=5)
+        for a in (one, many):
+            make_cam.run(a)
+            make_sem_seg_labels.run(a)
+            make_ins_seg_labels.run(a)
+    finally:
+        _common.make_dataset = real
+    _same_tree(one.cam_out_dir, many.cam_out_dir, names, "npy")
+    _same_tree(one.sem_seg_out_dir, many.sem_seg_out_dir, names, "png")
+    _same_tree(one.ins_seg_out_dir, many.ins_seg_out_dir, names, "npy")
+
+
+_SPAWN_CHILD = """
+import os, sys, types, pickle
+sys.path.insert(0, {root!r})
+import torch
+from irn_b200.step import make_cam, make_sem_seg_labels, make_ins_seg_labels
+args = pickle.load(open({args!r}, 'rb'))
+make_cam.run(args); make_sem_seg_labels.run(args); make_ins_seg_labels.run(args)
+"""
+
+
+def test_spawn_branch_matches_single_gpu(voc_tree, tmp_path):
+    """The reference's multi-GPU seam (step/make_cam.py:67-74: stride split + torch.multiprocessing.spawn, one process per
+    GPU) on every visible GPU, byte-compared with the same run restricted to one GPU."""
+    import pickle
+    import subprocess
+    import sys
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    _, _, args = voc_tree
+    names = ["2007_%06d" % i for i in range(6)]
+    runs = {}
+    for tag, visible in (("multi", None), ("single", "0")):
+        a = _copy_args(args, str(tmp_path), tag, synthetic=6, step_batch=2, exp_times=5, num_workers=0)
+        pickle.dump(a, open(tmp_path / (tag + ".pkl"), "wb"))
+        env = dict(os.environ, PYTHONPATH=ROOT)
+        if visible is not None:
+            env["CUDA_VISIBLE_DEVICES"] = visible
+        r = subprocess.run([sys.executable, "-c", _SPAWN_CHILD.format(root=ROOT, args=str(tmp_path / (tag + ".pkl")))], env=env,
+                           capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+        assert r.returncode == 0, r.stderr[-3000:]
+        runs[tag] = a
+    _same_tree(runs["multi"].cam_out_dir, runs["single"].cam_out_dir, names, "npy")
+    _same_tree(runs["multi"].sem_seg_out_dir, runs["single"].sem_seg_out_dir, names, "png")
+    _same_tree(runs["multi"].ins_seg_out_dir, runs["single"].ins_seg_out_dir, names, "npy")
 
 
 def test_run_sample_cli_synthetic(tmp_path, cuda_dev):

@@ -71,3 +71,36 @@ def test_run_sample_flag_table():
     assert len(names) == len(set(names)) and {"device_pyramid", "synthetic", "cam_scales", "beta", "exp_times"} <= set(names)
     assert run_sample._bool("False") is False and run_sample._bool("true") is True
     assert run_sample._scales("1.0,0.5") == (1.0, 0.5)
+
+
+def test_spawn_arguments_pickle():
+    """What `torch.multiprocessing.spawn(_work, args=(model, shards, args))` has to pickle when there is more than one GPU
+    (step/make_cam.py:74): the model (parameter holder, no device plan yet), the strided shards of both dataset kinds,
+    the argument namespace -- and the shards must still yield items after the round trip."""
+    import pickle
+    from irn_b200.cam import CAM
+    from irn_b200.irn import EdgeDisplacement
+    args = types.SimpleNamespace(synthetic=6, voc12_root="", num_workers=0, cam_scales=(1.0, 0.5))
+    shards = torchutils.split_dataset(_common.make_dataset(args, "unused", args.cam_scales), 2)
+    for model in (CAM(), EdgeDisplacement()):
+        model.load_state_dict(model.state_dict())
+        blob = pickle.dumps((model, shards, args))
+        m2, s2, a2 = pickle.loads(blob)
+        assert len(m2.state_dict()) == len(model.state_dict()) and m2._plan is None
+        assert [len(s) for s in s2] == [3, 3] and s2[1][0]["name"] == "2007_000001"
+        assert s2[0][1]["img_u8"].shape == (512, 512, 3) and a2.synthetic == 6
+
+
+def test_synthetic_names_are_the_same_for_every_step(tmp_path):
+    """--synthetic: make_cam (reads --train_list in the reference) and the label steps (--infer_list) must see the same ids,
+    whatever list files happen to exist in the working directory; --synthetic_list names them explicitly."""
+    (tmp_path / "train_aug.txt").write_text("2007_000032\n2007_000039\n")
+    (tmp_path / "train.txt").write_text("2008_000001\n2008_000002\n")
+    args = types.SimpleNamespace(synthetic=2, voc12_root="")
+    a = _common.make_dataset(args, str(tmp_path / "train_aug.txt"), (1.0,))
+    b = _common.make_dataset(args, str(tmp_path / "train.txt"), (1.0,))
+    assert [a[i]["name"] for i in range(2)] == [b[i]["name"] for i in range(2)] == ["2007_000000", "2007_000001"]
+    args.synthetic_list = str(tmp_path / "train_aug.txt")
+    c = _common.make_dataset(args, str(tmp_path / "train.txt"), (1.0,))
+    assert [c[i]["name"] for i in range(2)] == ["2007_000032", "2007_000039"]
+    assert _common.step_batch(args) == _common.DEFAULT_STEP_BATCH and _common.step_batch(types.SimpleNamespace(step_batch=1)) == 1

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_path
+from conftest import golden_path, check_detections, unpack_masks
 from oracle import indexing as oi
 from oracle import nets, steps
 from irn_b200 import synth
@@ -130,6 +130,66 @@ def test_step_bodies_oracle():
         ref = g["sem%d" % i]
         assert lab.shape == ref.shape
         assert (lab != ref).mean() < 2e-3   # pixels on a decision boundary may flip (float walk differs at 1e-5)
+
+
+def test_detect_instance_oracle_vs_reference_outputs():
+    """oracle.steps.detect_instance / ins_seg_labels (step/make_ins_seg_labels.py:82-105,131-150) against the dicts the
+    reference's own `_work` loop saved: detection count, class order, scores (1e-4) and masks."""
+    g = np.load(golden_path("steps.npz"))
+    irn_sd = synth.irn_state_dict()
+    for i in range(len(g["ids"])):
+        img = g["img%d" % i]
+        H, W = img.shape[:2]
+        x = synth.normalize_image(img)
+        with torch.no_grad():
+            edge, dp = nets.edge_displacement(torch.from_numpy(np.stack([x, x[..., ::-1].copy()])), irn_sd)
+        det = steps.ins_seg_labels(g["cam_cam%d" % i], g["cam_keys%d" % i], edge.numpy(), dp.numpy(), (H, W))
+        check_detections(det, g["ins_score%d" % i], unpack_masks(g, str(i)), g["ins_class%d" % i])
+
+
+def test_detect_instance_oracle_exact_on_reference_masks():
+    """detect_instance alone, fed the reference's own masks back as the argmax one-hot: segments, order and areas must
+    reproduce exactly (integer work)."""
+    g = np.load(golden_path("steps.npz"))
+    for i in range(len(g["ids"])):
+        ref_mask, ref_class, ref_score = unpack_masks(g, str(i)), g["ins_class%d" % i], g["ins_score%d" % i]
+        # rebuild the per-channel masks: union of the reference's segments per (class, instance) channel is not stored, but
+        # every segment is one connected component, so feeding each segment as its own channel must return it unchanged
+        scores = ref_mask.astype(np.float32) * ref_score[:, None, None]
+        det = steps.detect_instance(scores, ref_mask, ref_class, max_fragment_size=0)
+        assert np.array_equal(det["mask"], ref_mask) and np.array_equal(det["class"], ref_class)
+        assert np.array_equal(det["score"][ref_score > 0], ref_score[ref_score > 0])
+
+
+def test_oracle_at_benchmark_size_512():
+    """The oracle's label tail and ins-seg tail at the benchmark's size, fed the reference's own 128x128 walk outputs /
+    CAMs / edge / dp for one 512x512 image (tests/golden/steps512.npz): labels identical, detections identical."""
+    g = np.load(golden_path("steps512.npz"))
+    lab = steps.sem_seg_labels(torch.from_numpy(g["walk_sem"]), g["cam_keys"], (512, 512))
+    assert (lab != g["sem"]).mean() == 0.0
+    # exact-operator walk vs the reference's dense fp32 walk at 128x128 / 256 steps (SURVEY.md App. B: < 1e-4)
+    st = oi.propagate_stencil(g["cam_cam"], g["edge"], 5, 10, 256)
+    assert np.abs(st.reshape(g["walk_sem"].shape) - g["walk_sem"]).max() < 1e-4
+    det = steps.ins_seg_labels(g["cam_cam"], g["cam_keys"], g["edge"], g["dp"], (512, 512),
+                               walk=lambda seeds, edge: g["walk_ins"][:, 0])
+    check_detections(det, g["ins_score"], unpack_masks(g), g["ins_class"], score_tol=1e-6, pixel_tol=1e-9)
+
+
+def test_oracle_nets_at_benchmark_size_512():
+    """oracle.nets CAM forward at the four benchmark input sizes (256/512/768/1024) and EdgeDisplacement at 512, against the
+    reference's own forwards inside its make_cam / make_sem_seg loops."""
+    from oracle import pipeline as opipe
+    g = np.load(golden_path("steps512.npz"))
+    img = synth.image(int(g["seed"]), 512, 512)
+    cam_sd, irn_sd = synth.cam_state_dict(), synth.irn_state_dict()
+    xs = opipe.msf_inputs(img, (1.0, 0.5, 1.5, 2.0))
+    with torch.no_grad():
+        for x in xs:
+            y = nets.cam_forward(x, cam_sd).numpy()
+            ref = g["camscale_%d" % x.shape[-1]]
+            assert np.abs(y - ref).max() / ref.max() < 1e-5
+        e, d = nets.edge_displacement(xs[0], irn_sd)
+    assert np.abs(e.numpy() - g["edge"]).max() < 1e-5 and np.abs(d.numpy() - g["dp"]).max() < 1e-4
 
 
 def test_split_indices():
