@@ -136,6 +136,7 @@ void irn_net_destroy(irn_net* net);
  * product) for every conv with Cin % 32 == 0 and Cout % 64 == 0, SIMT fp32 for the rest; 0 = SIMT IEEE fp32
  * everywhere (the on-device cross-check). */
 int irn_net_set_conv_mode(irn_net* net, int mode);
+int irn_net_get_conv_mode(const irn_net* net);
 
 /* One convolution (+ folded FixedBatchNorm, residual add, ReLU) as a plan of its own: the building block of
  * the two networks above (net/resnet50.py:34-54), exposed for unit tests and for wiring other topologies.

@@ -33,6 +33,14 @@ class CAM(CamParams):
     def __init__(self):
         super().__init__()
         self._plan = None
+        self._conv_mode = None      # None = the library's default for this network
+
+    def set_conv_mode(self, mode):
+        """Convolution arithmetic of the native plan: 0 SIMT fp32, 1 tcgen05 3xTF32, 2 tcgen05 bf16x3 (irn_net_set_conv_mode)."""
+        self._conv_mode = None if mode is None else int(mode)
+        if self._plan is not None and self._conv_mode is not None:
+            _lib.check(_lib.lib().irn_net_set_conv_mode(self._plan.handle, self._conv_mode), "irn_net_set_conv_mode")
+        return self
 
     # the reference's Net.train() ignores `mode` (net/resnet50_cam.py:39-43); inference only here
     def train(self, mode=True):
@@ -52,6 +60,8 @@ class CAM(CamParams):
             with torch.cuda.device(device):
                 _lib.check(_lib.lib().irn_cam_net_create(blob.ctypes.data, blob.size, ctypes.byref(h)), "irn_cam_net_create")
             self._plan = _Plan(h, device)
+            if self._conv_mode is not None:
+                _lib.check(_lib.lib().irn_net_set_conv_mode(h, self._conv_mode), "irn_net_set_conv_mode")
         return self._plan
 
     def forward_batch(self, x):

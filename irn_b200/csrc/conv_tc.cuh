@@ -41,6 +41,7 @@ struct TcArgs {
     float* out;
     int B, Ho, Wo, Cout, Cin, ksize, stride, pad, relu;
     int tiles_x, tiles_y;
+    const float* oscale = nullptr;   // conv_f16.cuh only: per-output-channel factor undoing the weights' power-of-two pre-scale
     int mode;   // 0: NHWC input, one k-block per (tap, 32-channel slice); 1: stem, NHWC4 zero-haloed input, one k-block per filter row
 };
 
@@ -1030,6 +1031,7 @@ conv_tc_persist_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args
     }
 }
 
+#ifdef IRN_EXPERIMENTAL   // CTA-pair weight multicast variant of the long-K kernel: measured no gain (profiles/r01_conv_micro_final.txt)
 // ---- 2-CTA cluster helpers (weight tile multicast)
 __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;
@@ -1256,5 +1258,7 @@ conv_tc_ts2_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     }
 }
 
+
+#endif  // IRN_EXPERIMENTAL
 
 }  // namespace irn

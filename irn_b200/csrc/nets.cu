@@ -7,6 +7,8 @@
 // transposed to [kh*kw*Cin][Cout] for the SIMT kernel.  Activations are NHWC fp32 in a caller-provided
 // workspace.  The host walks the fixed topology and enqueues kernels on the caller's stream; nothing
 // synchronises.
+#include <cuda_fp16.h>
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -15,6 +17,7 @@
 #include "common.h"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
+#include "conv_f16.cuh"
 
 namespace irn {
 
@@ -28,6 +31,13 @@ struct Conv {
     int bn = 0;              // N tile (64 or 128); 0 = not eligible
     CUtensorMap map_bhi, map_blo;        // box {32, bn}
     CUtensorMap map_bhi64, map_blo64;    // box {32, 64} (short-K configuration)
+    // f16x3 path (conv_f16.cuh): weights [cout][k*k*cin], pre-scaled per output channel by a power of two and split into fp16
+    // hi / lo parts, boxes {64 k, 64 | 128 | 256 rows}; oscale[cout] = the inverse scale applied in the epilogue
+    uint16_t* wb_hi = nullptr;
+    uint16_t* wb_lo = nullptr;
+    float* oscale = nullptr;
+    bool bf_ok = false;
+    CUtensorMap map_bf_hi[3], map_bf_lo[3];   // N tile 64, 128, 256 (the latter two only when cout allows)
     bool stem_tc = false;    // 7x7/s2 stem repacked as 7 k-blocks of (8 taps x 4 channels) over a zero-haloed NHWC4 input
 };
 
@@ -93,6 +103,8 @@ static int upload(irn_net* net, const std::vector<float>& h, float** out) {
     return kOk;
 }
 
+static int make_bf16_weights(irn_net* net, Conv& c, const std::vector<float>& wt);
+
 // Reads conv weight [cout][cin][k][k] (+ optional BN gamma, beta, mean, var) and uploads the folded,
 // transposed tensors.  Fold: y = (conv - mean) / sqrt(var + 1e-5) * gamma + beta  (net/resnet50.py:11-14).
 static int read_conv(irn_net* net, Reader& rd, Conv& c, int cin, int cout, int k, int stride, int pad, bool bn) {
@@ -121,6 +133,7 @@ static int read_conv(irn_net* net, Reader& rd, Conv& c, int cin, int cout, int k
     int rc = upload(net, wt, &c.wt);
     if (rc) return rc;
     if (bn && (rc = upload(net, bias, &c.bias))) return rc;
+    if ((rc = make_bf16_weights(net, c, wt))) return rc;
     // tensor-core eligibility: 32-channel k slices, 64/128-wide N tiles, 1x1 or 3x3, stride 1 or 2
     c.bn = (cout % 128 == 0) ? 128 : (cout % 64 == 0 ? 64 : 0);
     if (cin % kTcBK != 0 || !(k == 1 || k == 3) || !(stride == 1 || stride == 2)) c.bn = 0;
@@ -150,6 +163,51 @@ static int read_conv(irn_net* net, Reader& rd, Conv& c, int cin, int cout, int k
         const uint32_t box64[2] = {(uint32_t)kTcBK, 64};
         if ((rc = make_tensor_map(&c.map_bhi64, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_hi, dims, strides, box64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
         if ((rc = make_tensor_map(&c.map_blo64, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_lo, dims, strides, box64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    }
+    return kOk;
+}
+
+// fp16 hi / lo planes of the folded weights, [cout][K] K-major, + tensor maps for 64- / 128- / 256-row tiles.  Every output
+// channel is first scaled by a power of two so that max |w| lies in [1,2): the lo parts stay clear of fp16's subnormal range
+// whatever FixedBatchNorm's gamma / sqrt(var) did to the channel, and the epilogue undoes the scale exactly.
+static int make_bf16_weights(irn_net* net, Conv& c, const std::vector<float>& wt /* [K][cout] */) {
+    const size_t K = (size_t)c.k * c.k * c.cin;
+    c.bf_ok = c.cin % kBfBK == 0 && c.cout % 64 == 0 && (c.k == 1 || c.k == 3) && (c.stride == 1 || c.stride == 2);
+    if (!c.bf_ok) return kOk;
+    std::vector<uint16_t> hi((size_t)c.cout * K), lo((size_t)c.cout * K);
+    std::vector<float> inv(c.cout, 1.0f);
+    for (int o = 0; o < c.cout; ++o) {
+        float mx = 0.f;
+        for (size_t kk = 0; kk < K; ++kk) mx = std::max(mx, std::fabs(wt[kk * c.cout + o]));
+        int e = 1;
+        if (mx > 0.f && std::isfinite(mx)) std::frexp(mx, &e);          // mx = m * 2^e, m in [0.5, 1)
+        const int sh = 1 - e;                                           // w * 2^sh has its maximum in [1, 2)
+        inv[o] = std::ldexp(1.0f, -sh);
+        for (size_t kk = 0; kk < K; ++kk) {
+            const float v = std::ldexp(wt[kk * c.cout + o], sh);
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn(v - __half2float(h));
+            hi[(size_t)o * K + kk] = __half_as_ushort(h);
+            lo[(size_t)o * K + kk] = __half_as_ushort(l);
+        }
+    }
+    int rc = upload(net, inv, &c.oscale);
+    if (rc) return rc;
+    for (int part = 0; part < 2; ++part) {
+        void* d = nullptr;
+        IRN_CUDA(cudaMalloc(&d, hi.size() * sizeof(uint16_t)));
+        net->allocs.push_back(d);
+        IRN_CUDA(cudaMemcpy(d, part == 0 ? hi.data() : lo.data(), hi.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        (part == 0 ? c.wb_hi : c.wb_lo) = (uint16_t*)d;
+    }
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)c.cout};
+    const uint64_t strides[1] = {(uint64_t)K * sizeof(uint16_t)};
+    for (int i = 0; i < 3; ++i) {
+        const uint32_t rows = 64u << i;
+        if (c.cout % rows != 0) continue;
+        const uint32_t box[2] = {(uint32_t)kBfBK, rows};
+        if ((rc = make_tensor_map(&c.map_bf_hi[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.wb_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+        if ((rc = make_tensor_map(&c.map_bf_lo[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.wb_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     }
     return kOk;
 }
@@ -377,6 +435,7 @@ static int launch_tc_ts(const Conv& c, const float* in, int B, int H, int W, int
     a.tiles_x = (Wo + kTcTW - 1) / kTcTW;
     a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
     a.mode = 0;
+#ifdef IRN_EXPERIMENTAL
     static const int use_pair = getenv("IRN_TC_PAIR") ? atoi(getenv("IRN_TC_PAIR")) : 0;   // measured: no gain (1322 vs 1323 us on the 3x3x512 layer), kept for A/B
     if (use_pair) {
         static DeviceOnce once2;
@@ -393,10 +452,64 @@ static int launch_tc_ts(const Conv& c, const float* in, int B, int H, int W, int
         IRN_LAUNCH_CHECK("conv_tc_ts2_kernel");
         return kOk;
     }
+#endif
     dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B * (c.cout / 128)));
     conv_tc_ts_kernel<<<grid, kTsThreads, kTsSmem, st>>>(maps, a);
     IRN_LAUNCH_CHECK("conv_tc_ts_kernel");
     return kOk;
+}
+
+template <int BN, int NACC>
+static int launch_bf16(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
+                       cudaStream_t st) {
+    using Cfg = BfCfg<BN, NACC>;
+    static DeviceOnce once;
+    const int ds = once.slot();
+    if (once.need(ds)) {
+        IRN_CUDA(cudaFuncSetAttribute((conv_f16_kernel<BN, NACC>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+        int dev = 0;
+        IRN_CUDA(cudaGetDevice(&dev));
+        IRN_CUDA(cudaDeviceGetAttribute(&once.n_sm[ds], cudaDevAttrMultiProcessorCount, dev));
+        once.done[ds] = true;
+    }
+    if (BN == 256 && residual) return fail(kUnsupported, "conv_f16_kernel<256>: no residual input (dispatch error)");
+    const int mi = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
+    TcMaps maps;
+    maps.b_hi = c.map_bf_hi[mi];
+    maps.b_lo = c.map_bf_lo[mi];
+    const uint64_t dims[4] = {(uint64_t)c.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)c.cin * 4, (uint64_t)W * c.cin * 4, (uint64_t)H * W * c.cin * 4};
+    const uint32_t box[4] = {32u, (uint32_t)(kTcTW * c.stride), (uint32_t)(kTcTH * c.stride), 1};
+    const uint32_t estr[4] = {1, (uint32_t)c.stride, (uint32_t)c.stride, 1};
+    int rc = make_tensor_map(&maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, estr);
+    if (rc) return rc;
+    TcArgs a;
+    a.bias = c.bias; a.residual = residual; a.out = out;
+    a.oscale = c.oscale;
+    a.B = B; a.Ho = Ho; a.Wo = Wo; a.Cout = c.cout; a.Cin = c.cin; a.ksize = c.k; a.stride = c.stride; a.pad = c.pad;
+    a.relu = relu ? 1 : 0;
+    a.tiles_x = (Wo + kTcTW - 1) / kTcTW;
+    a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
+    static const int swap_dbg = getenv("IRN_BF_SWAP") ? atoi(getenv("IRN_BF_SWAP")) : 0;   // bring-up aid only
+    a.mode = swap_dbg ? 2 : 0;
+    const long long total = (long long)a.tiles_x * a.tiles_y * B * (c.cout / BN);
+    const int n_sm = once.n_sm[ds];
+    conv_f16_kernel<BN, NACC><<<(unsigned)(total < n_sm ? total : n_sm), kBfThreads, Cfg::kSmem, st>>>(maps, a);
+    IRN_LAUNCH_CHECK("conv_f16_kernel");
+    return kOk;
+}
+
+// f16x3 dispatch: the 256-wide tile for the long reductions without a residual (layer3/4 3x3, the 1024/2048-channel reductions,
+// the projection shortcuts), 128-wide double-buffered tiles for the rest, 64-wide for the 64-channel layers
+static int run_conv_bf16(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
+                         cudaStream_t st) {
+    const int K = c.k * c.k * c.cin;
+    static const int wide_min_k = getenv("IRN_BF_WIDE_MINK") ? atoi(getenv("IRN_BF_WIDE_MINK")) : 512;
+    // one accumulator per tile: on B200 separate accumulators for the hi*hi and the cross terms (NACC = 2, 3) change nothing
+    // measurable (tools/bf16_bringup.py, profiles/r02_conv_bf16x3_vs_f16x3.md) and cost TMEM / the epilogue overlap
+    if (c.cout % 256 == 0 && K >= wide_min_k && !residual) return launch_bf16<256, 1>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+    if (c.cout % 128 == 0) return launch_bf16<128, 1>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+    return launch_bf16<64, 1>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
 }
 
 static int run_conv(const irn_net* net, const Conv& c, const float* in, int B, int H, int W, const float* residual, float* out, bool relu,
@@ -408,7 +521,8 @@ static int run_conv(const irn_net* net, const Conv& c, const float* in, int B, i
     g.Cout = c.cout; g.k = c.k; g.stride = c.stride; g.pad = c.pad;
     if (Ho_) *Ho_ = g.Ho;
     if (Wo_) *Wo_ = g.Wo;
-    if (net->conv_mode == 1 && c.bn) {
+    if (net->conv_mode == 2 && c.bf_ok) return run_conv_bf16(c, in, B, H, W, g.Ho, g.Wo, residual, out, relu, st);
+    if (net->conv_mode >= 1 && c.bn) {
         // short reductions (K <= 256) are latency-bound per tile: 64-wide tiles with a 2-stage pipeline and two TMEM
         // accumulators let two CTAs share an SM; long reductions use the 3-stage, 3-accumulator configuration
         const int K = c.k * c.k * c.cin;
@@ -479,7 +593,7 @@ static TrunkShapes trunk_shapes(int B, int H, int W) {
 static int run_trunk(const irn_net* net, const float* x_nchw, int B, int H, int W, int Hin, int Win, Arena& ar, bool keep,
                      const float* feats[5], TrunkShapes& sh, cudaStream_t st) {
     sh = trunk_shapes(B, Hin, Win);
-    const bool stem_tc = net->conv_mode == 1 && net->stem.stem_tc;
+    const bool stem_tc = net->conv_mode >= 1 && net->stem.stem_tc;
     float* x_in = stem_tc ? ar.take((size_t)B * (Hin + 6) * (Win + 8) * 4) : ar.take((size_t)B * Hin * Win * 3);
     float* stem_out = ar.take((size_t)B * sh.H1 * sh.W1 * 64);
     float* pool_out = ar.take((size_t)B * sh.H2 * sh.W2 * 64);
@@ -585,16 +699,20 @@ extern "C" int irn_conv_forward(irn_conv* c, const float* in, int B, int H, int 
                                 irn_stream_t stream) {
     launch_counter() = 0;
     if (!c || !in || !out || B <= 0 || H <= 0 || W <= 0) return fail(kBadArg, "irn_conv_forward: bad argument");
+    if (mode < 0 || mode > 2) return fail(kBadArg, "irn_conv_forward: mode must be 0, 1 or 2");
     if (mode == 1 && c->conv.bn == 0) return fail(kUnsupported, "irn_conv_forward: this convolution is not eligible for the tensor-core kernel (Cin %% 32, Cout %% 64, k in {1,3}, stride in {1,2})");
+    if (mode == 2 && !c->conv.bf_ok) return fail(kUnsupported, "irn_conv_forward: this convolution is not eligible for the f16x3 kernel (Cin %% 64, Cout %% 64, k in {1,3}, stride in {1,2})");
     c->holder.conv_mode = mode;
     return run_conv(&c->holder, c->conv, in, B, H, W, residual, out, relu != 0, (cudaStream_t)stream, nullptr, nullptr);
 }
 
 extern "C" int irn_net_set_conv_mode(irn_net* net, int mode) {
-    if (!net || (mode != 0 && mode != 1)) return fail(kBadArg, "irn_net_set_conv_mode: mode must be 0 (SIMT fp32) or 1 (tcgen05 3xTF32)");
+    if (!net || mode < 0 || mode > 2) return fail(kBadArg, "irn_net_set_conv_mode: mode must be 0 (SIMT fp32), 1 (tcgen05 3xTF32) or 2 (tcgen05 f16x3)");
     net->conv_mode = mode;
     return kOk;
 }
+
+extern "C" int irn_net_get_conv_mode(const irn_net* net) { return net ? net->conv_mode : -1; }
 
 extern "C" void irn_net_destroy(irn_net* net) {
     if (!net) return;
@@ -672,7 +790,7 @@ extern "C" int irn_cam_forward(const irn_net* net, const float* x_nchw, int B, i
     int rc = run_trunk(net, x_nchw, B, H, W, H, W, ar, false, feats, sh, st);
     if (rc) return rc;
     const int P = B / 2, h = sh.Hl[3], w = sh.Wl[3];
-    if (net->conv_mode == 1 && net->cls_conv.bn) {
+    if (net->conv_mode >= 1 && net->cls_conv.bn) {
         // classifier as a 2048 -> 64 tensor-core conv with fused ReLU (the one-warp-per-pixel head re-reads the 160 KB weight
         // matrix per pixel), then flip-add + NHWC -> NCHW on the 20 real channels
         float* tmp = ar.take((size_t)B * h * w * 64);

@@ -387,6 +387,7 @@ rw_step_tma_kernel(const __grid_constant__ RwMaps maps, const double* __restrict
     }
 }
 
+#ifdef IRN_EXPERIMENTAL   // persistent ring variant of the per-step kernel: measured slower (profiles/r01_rw_experiments.md); not in the product build
 // ---------------------------------------------------------------- persistent ring step kernel (radius 5, experiment, variant 3)
 // Same arithmetic as rw_step_tma_kernel, restructured so that TMA latency is never exposed: one persistent CTA per SM
 // walks tiles b, b+G, b+2G, ...; warp 4 is a TMA producer that runs ahead through a ring of kRingW weight-class buffers and
@@ -531,6 +532,7 @@ rw_step_ring_kernel(const __grid_constant__ RwMaps maps, const double* __restric
         }
     }
 }
+#endif  // IRN_EXPERIMENTAL
 
 // ---------------------------------------------------------------- fused walk (radius 5, h,w <= 128): the production path
 // All n_iter steps of one (image, channel) in ONE launch, one thread-block cluster per item:
@@ -803,6 +805,9 @@ static int launch_tma_steps(const RwWorkspace& ws, int n_img, int totc, int h, i
         }
         return kOk;
     }
+#ifndef IRN_EXPERIMENTAL
+    return fail(kUnsupported, "irn_random_walk_variant: variant 3 (ring kernel) is an experiment, built only with -DIRN_EXPERIMENTAL");
+#else
     int dev = 0, n_sm = 0;
     IRN_CUDA(cudaGetDevice(&dev));
     IRN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -816,6 +821,7 @@ static int launch_tma_steps(const RwWorkspace& ws, int n_img, int totc, int h, i
         IRN_LAUNCH_CHECK("rw_step_ring_kernel");
     }
     return kOk;
+#endif
 }
 
 // Launches the fused walk; *launched = false when the device cannot co-schedule a cluster of the needed size (caller falls
@@ -939,8 +945,13 @@ static int walk_impl(const float* x, const float* edge, float* out, int n_img, c
             }
             IRN_CUDA(cudaEventRecord(g_rw_ev[0], stream));
         }
+#ifdef IRN_EXPERIMENTAL
         rc = variant == 5 ? launch_fused<2>(ws, x, edge, out, totc, h, w, n_iter, stream, &fused, &n_fused_clusters)
                           : launch_fused<4>(ws, x, edge, out, totc, h, w, n_iter, stream, &fused, &n_fused_clusters);
+#else
+        if (variant == 5) return fail(kUnsupported, "irn_random_walk_variant: variant 5 (two rows per thread) is an experiment, built only with -DIRN_EXPERIMENTAL");
+        rc = launch_fused<4>(ws, x, edge, out, totc, h, w, n_iter, stream, &fused, &n_fused_clusters);
+#endif
         if (rc) return rc;
         if (fused && g_rw_timing) {
             IRN_CUDA(cudaEventRecord(g_rw_ev[1], stream));

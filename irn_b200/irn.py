@@ -22,6 +22,14 @@ class EdgeDisplacement(IrnParams):
         self.crop_size = crop_size
         self.stride = stride
         self._plan = None
+        self._conv_mode = None
+
+    def set_conv_mode(self, mode):
+        """0 SIMT fp32, 1 tcgen05 3xTF32 (default: the edge head needs it for the 1e-4 contract), 2 tcgen05 bf16x3."""
+        self._conv_mode = None if mode is None else int(mode)
+        if self._plan is not None and self._conv_mode is not None:
+            _lib.check(_lib.lib().irn_net_set_conv_mode(self._plan.handle, self._conv_mode), "irn_net_set_conv_mode")
+        return self
 
     def load_state_dict(self, *a, **k):
         self._plan = None
@@ -34,6 +42,8 @@ class EdgeDisplacement(IrnParams):
             with torch.cuda.device(device):
                 _lib.check(_lib.lib().irn_irn_net_create(blob.ctypes.data, blob.size, ctypes.byref(h)), "irn_irn_net_create")
             self._plan = _Plan(h, device)
+            if self._conv_mode is not None:
+                _lib.check(_lib.lib().irn_net_set_conv_mode(h, self._conv_mode), "irn_net_set_conv_mode")
         return self._plan
 
     def forward_batch(self, x):

@@ -25,7 +25,7 @@ from .. import preprocess
 from ..misc import torchutils
 from ..voc12 import dataloader as voc_data
 
-DEFAULT_STEP_BATCH = 16
+DEFAULT_STEP_BATCH = 32
 
 
 def collate_one(batch):
@@ -52,7 +52,7 @@ def device_pyramid(args):
 
 
 def step_batch(args):
-    """--step_batch N (default 16): images of equal size processed together; 1 = the reference's one-image loop."""
+    """--step_batch N (default 32): images of equal size processed together; 1 = the reference's one-image loop."""
     return max(1, int(getattr(args, "step_batch", DEFAULT_STEP_BATCH) or 1))
 
 
@@ -100,10 +100,16 @@ class Writer:
         return s
 
     def to_host(self, tensors):
-        """Device tensors -> host tensors through this thread's side stream (call from inside a job)."""
+        """Device tensors -> host tensors through this thread's side stream (call from inside a job, i.e. after the
+        producing work has completed).  An entry that is a list of tensors is concatenated along dim 0 first -- on the same
+        side stream, so the copy is ordered after the concatenation."""
         s = self.stream()
         with torch.cuda.stream(s):
-            out = [t.to("cpu", non_blocking=True) if t is not None else None for t in tensors]
+            out = []
+            for t in tensors:
+                if isinstance(t, (list, tuple)):
+                    t = torch.cat(list(t), 0) if len(t) > 1 else t[0]
+                out.append(t.to("cpu", non_blocking=True) if t is not None else None)
         s.synchronize()
         return out
 

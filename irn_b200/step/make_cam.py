@@ -21,7 +21,7 @@ def cam_one_image(model, pack, args):
 def _save(ctx, names, keys, strided, highres, out_dir):
     """Pool thread: one device->host copy per tensor kind for the whole batch, then one np.save per image."""
     counts = [int(k.size) for k in keys]
-    lo, hi = ctx.writer.to_host([torch.cat(strided, 0), torch.cat(highres, 0)])
+    lo, hi = ctx.writer.to_host([strided, highres])
     o = 0
     for name, k, c in zip(names, keys, counts):
         np.save(os.path.join(out_dir, name + ".npy"),

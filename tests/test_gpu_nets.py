@@ -29,16 +29,19 @@ def irn_model(cuda_dev):
     return m
 
 
-def test_cam_forward_vs_reference(cuda_dev, cam_model):
+@pytest.mark.parametrize("mode", [1, 2], ids=["tf32x3", "f16x3"])
+def test_cam_forward_vs_reference(cuda_dev, cam_model, mode):
     g = np.load(golden_path("cam_forward.npz"))
+    cam_model.set_conv_mode(mode)
     for i in range(3):
         y = cam_model(torch.from_numpy(g["x%d" % i]).to(cuda_dev)).cpu().numpy()
         ref = g["y%d" % i]
         assert y.shape == ref.shape
         scale = ref.max()
         err = np.abs(y - ref).max() / scale
-        record("cam_forward_vs_reference", input=list(g["x%d" % i].shape[-2:]), normalised_err=err)
+        record("cam_forward_vs_reference", input=list(g["x%d" % i].shape[-2:]), normalised_err=err, conv_mode=mode)
         assert err < 1e-4, "normalised CAM err %g" % err
+    cam_model.set_conv_mode(None)
 
 
 def test_cam_batch_equals_single(cuda_dev, cam_model):
@@ -67,8 +70,7 @@ def test_edge_displacement_vs_reference(cuda_dev, irn_model):
         d_max = np.abs(g["dp%d" % i]).max()
         record("edge_displacement_vs_reference", input=list(x.shape[-2:]), edge_err=e_err, dp_err=d_err, dp_absmax=d_max)
         assert e_err < 1e-4                               # edge is a sigmoid output in (0,1): absolute = relative to full scale
-        # dp is an unbounded displacement in stride-4 pixels: the 1e-4 contract is held relative to the field's own range
-        assert d_err < 1e-4 * max(1.0, d_max), "dp err %g with |dp|max %g" % (d_err, d_max)
+        assert d_err < 1e-4, "dp err %g (|dp|max %g)" % (d_err, d_max)       # absolute, in stride-4 pixels (measured ~2e-5 on B200)
 
 
 def test_state_dict_keys_match_reference_format(cam_model, irn_model):

@@ -33,7 +33,7 @@ def test_edge_to_affinity_exact(cuda_dev):
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(golden_path("rw_*.npz"))), ids=os.path.basename)
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4])
 def test_random_walk_vs_reference(cuda_dev, path, variant):
     g = np.load(path)
     x, edge = g["x"], g["edge"]
@@ -69,11 +69,11 @@ def test_walk_shapes_and_properties(cuda_dev, h, w):
     a = run(0)
     fits = h <= 128 and w <= 128
     assert indexing.last_walk_was_fused() == fits
-    b, s2, c = run(1), run(2), run(3)
+    b, s2 = run(1), run(2)
     assert np.abs(a - b).max() < 1e-6
-    assert np.array_equal(a, s2) and np.array_equal(a, c)   # fused, two-buffer and ring kernels do identical arithmetic
+    assert np.array_equal(a, s2)   # fused and per-step kernels do identical arithmetic
     if fits:
-        assert np.array_equal(a, run(4)) and np.array_equal(a, run(5))
+        assert np.array_equal(a, run(4))
         for n in (0, 1, 3):   # odd / zero step counts exercise both state buffers
             assert np.array_equal(run(4, n), run(2, n))
     else:

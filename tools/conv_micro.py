@@ -21,6 +21,7 @@ LAYERS = [  # name, cin, cout, k, stride, H(in), B, residual
     ("L3 ds 512->1024 s2", 512, 1024, 1, 2, 128, 16, False),
 ]
 dev = torch.device("cuda:0")
+MODE = int(os.environ.get("CONV_MODE", "1"))
 only = os.environ.get("CONV_ONLY")
 if only:
     LAYERS = [l for l in LAYERS if any(o in l[0] for o in only.split(','))]
@@ -32,13 +33,13 @@ for name, cin, cout, k, s, H, B, res in LAYERS:
     Ho = (H + 2 * (k // 2) - k) // s + 1
     r = torch.randn(B, Ho, Ho, cout, device=dev) if res else None
     for _ in range(3):
-        conv(x, r, relu=True, mode=1)
+        conv(x, r, relu=True, mode=MODE)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     n = 10
     for _ in range(n):
-        conv(x, r, relu=True, mode=1)
+        conv(x, r, relu=True, mode=MODE)
     e1.record(); torch.cuda.synchronize()
     us = 1e3 * e0.elapsed_time(e1) / n
     fl = 2.0 * B * Ho * Ho * cin * cout * k * k
