@@ -32,12 +32,12 @@ struct Conv {
     CUtensorMap map_bhi, map_blo;        // box {32, bn}
     CUtensorMap map_bhi64, map_blo64;    // box {32, 64} (short-K configuration)
     // f16x3 path (conv_f16.cuh): weights [cout][k*k*cin], pre-scaled per output channel by a power of two and split into fp16
-    // hi / lo parts, boxes {64 k, 64 | 128 | 256 rows}; oscale[cout] = the inverse scale applied in the epilogue
+    // hi / lo parts, boxes {64 k, 64 | 128 rows}; oscale[cout] = the inverse scale applied in the epilogue
     uint16_t* wb_hi = nullptr;
     uint16_t* wb_lo = nullptr;
     float* oscale = nullptr;
     bool bf_ok = false;
-    CUtensorMap map_bf_hi[3], map_bf_lo[3];   // N tile 64, 128, 256 (the latter two only when cout allows)
+    CUtensorMap map_bf_hi[2], map_bf_lo[2];   // N tile 64, 128 (the latter only when cout allows)
     bool stem_tc = false;    // 7x7/s2 stem repacked as 7 k-blocks of (8 taps x 4 channels) over a zero-haloed NHWC4 input
 };
 
@@ -57,7 +57,7 @@ struct Block {
 
 struct irn_net {
     int kind = 0;   // 0 = CAM, 1 = IRN (EdgeDisplacement)
-    int conv_mode = 1;   // 0 = SIMT exact-fp32 convolutions only, 1 = tcgen05 3xTF32 where eligible
+    int conv_mode = 2;   // 0 = SIMT exact-fp32 convolutions only, 1 = tcgen05 3xTF32 where eligible, 2 = tcgen05 f16x3 (default; 3xTF32 / SIMT for the layers it cannot take)
     irn::Conv stem;
     std::vector<irn::Block> blocks[4];
     // CAM
@@ -167,7 +167,7 @@ static int read_conv(irn_net* net, Reader& rd, Conv& c, int cin, int cout, int k
     return kOk;
 }
 
-// fp16 hi / lo planes of the folded weights, [cout][K] K-major, + tensor maps for 64- / 128- / 256-row tiles.  Every output
+// fp16 hi / lo planes of the folded weights, [cout][K] K-major, + tensor maps for 64- / 128-row tiles.  Every output
 // channel is first scaled by a power of two so that max |w| lies in [1,2): the lo parts stay clear of fp16's subnormal range
 // whatever FixedBatchNorm's gamma / sqrt(var) did to the channel, and the epilogue undoes the scale exactly.
 static int make_bf16_weights(irn_net* net, Conv& c, const std::vector<float>& wt /* [K][cout] */) {
@@ -202,7 +202,7 @@ static int make_bf16_weights(irn_net* net, Conv& c, const std::vector<float>& wt
     }
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)c.cout};
     const uint64_t strides[1] = {(uint64_t)K * sizeof(uint16_t)};
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 2; ++i) {
         const uint32_t rows = 64u << i;
         if (c.cout % rows != 0) continue;
         const uint32_t box[2] = {(uint32_t)kBfBK, rows};
@@ -459,28 +459,37 @@ static int launch_tc_ts(const Conv& c, const float* in, int B, int H, int W, int
     return kOk;
 }
 
-template <int BN, int NACC>
-static int launch_bf16(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
-                       cudaStream_t st) {
-    using Cfg = BfCfg<BN, NACC>;
+// ---- f16x3 kernels (conv_f16.cuh)
+static int f16_mode_flags() {
+    static const int spin = getenv("IRN_F16_SPIN") ? atoi(getenv("IRN_F16_SPIN")) : 1;     // 0: suspending try_wait on the critical path (A/B runs)
+    return spin ? 0 : 4;
+}
+
+template <int BN, int NACC, int NSLOT, bool HALO>
+static int launch_f16(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
+                      cudaStream_t st) {
+    using Cfg = F16Cfg<BN, NACC, NSLOT>;
+    constexpr size_t smem = HALO ? Cfg::kSmemHalo : Cfg::kSmem;
     static DeviceOnce once;
     const int ds = once.slot();
     if (once.need(ds)) {
-        IRN_CUDA(cudaFuncSetAttribute((conv_f16_kernel<BN, NACC>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+        if (HALO)
+            IRN_CUDA(cudaFuncSetAttribute((conv_f16_halo_kernel<BN, NACC, NSLOT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else
+            IRN_CUDA(cudaFuncSetAttribute((conv_f16_kernel<BN, NACC, NSLOT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int dev = 0;
         IRN_CUDA(cudaGetDevice(&dev));
         IRN_CUDA(cudaDeviceGetAttribute(&once.n_sm[ds], cudaDevAttrMultiProcessorCount, dev));
         once.done[ds] = true;
     }
-    if (BN == 256 && residual) return fail(kUnsupported, "conv_f16_kernel<256>: no residual input (dispatch error)");
-    const int mi = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
+    const int mi = BN == 64 ? 0 : 1;
     TcMaps maps;
     maps.b_hi = c.map_bf_hi[mi];
     maps.b_lo = c.map_bf_lo[mi];
     const uint64_t dims[4] = {(uint64_t)c.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)c.cin * 4, (uint64_t)W * c.cin * 4, (uint64_t)H * W * c.cin * 4};
-    const uint32_t box[4] = {32u, (uint32_t)(kTcTW * c.stride), (uint32_t)(kTcTH * c.stride), 1};
-    const uint32_t estr[4] = {1, (uint32_t)c.stride, (uint32_t)c.stride, 1};
+    const uint32_t box[4] = {32u, (uint32_t)(HALO ? kHaloW : kTcTW * c.stride), (uint32_t)(HALO ? kHaloH : kTcTH * c.stride), 1};
+    const uint32_t estr[4] = {1, (uint32_t)(HALO ? 1 : c.stride), (uint32_t)(HALO ? 1 : c.stride), 1};
     int rc = make_tensor_map(&maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, estr);
     if (rc) return rc;
     TcArgs a;
@@ -490,26 +499,45 @@ static int launch_bf16(const Conv& c, const float* in, int B, int H, int W, int 
     a.relu = relu ? 1 : 0;
     a.tiles_x = (Wo + kTcTW - 1) / kTcTW;
     a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
-    static const int swap_dbg = getenv("IRN_BF_SWAP") ? atoi(getenv("IRN_BF_SWAP")) : 0;   // bring-up aid only
-    a.mode = swap_dbg ? 2 : 0;
+    a.mode = f16_mode_flags();
     const long long total = (long long)a.tiles_x * a.tiles_y * B * (c.cout / BN);
     const int n_sm = once.n_sm[ds];
-    conv_f16_kernel<BN, NACC><<<(unsigned)(total < n_sm ? total : n_sm), kBfThreads, Cfg::kSmem, st>>>(maps, a);
-    IRN_LAUNCH_CHECK("conv_f16_kernel");
+    const unsigned grid = (unsigned)(total < n_sm ? total : n_sm);
+    if (HALO) {
+        conv_f16_halo_kernel<BN, NACC, NSLOT><<<grid, kBfThreads, smem, st>>>(maps, a);
+        IRN_LAUNCH_CHECK("conv_f16_halo_kernel");
+    } else {
+        conv_f16_kernel<BN, NACC, NSLOT><<<grid, kBfThreads, smem, st>>>(maps, a);
+        IRN_LAUNCH_CHECK("conv_f16_kernel");
+    }
     return kOk;
 }
 
-// f16x3 dispatch: the 256-wide tile for the long reductions without a residual (layer3/4 3x3, the 1024/2048-channel reductions,
-// the projection shortcuts), 128-wide double-buffered tiles for the rest, 64-wide for the 64-channel layers
+// f16x3 dispatch.  Reductions with K >= 512 keep the hi*hi and the cross terms in separate TMEM accumulators (the tensor core's
+// accumulate truncates: conv_f16.cuh, f16_issue3), shorter ones use one accumulator per tile and two accumulator sets so that the
+// epilogue of a tile overlaps the next tile's mainloop (they are memory-bound).  3x3 / stride 1 convs take the halo-tile kernel.
+template <bool HALO>
+static int dispatch_f16(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
+                        cudaStream_t st) {
+    const int K = c.k * c.k * c.cin;
+    static const int acc_min_k = getenv("IRN_F16_ACC_MINK") ? atoi(getenv("IRN_F16_ACC_MINK")) : 512;
+    static const int nslot = getenv("IRN_F16_NSLOT") ? atoi(getenv("IRN_F16_NSLOT")) : 4;      // 2: round-2's first version (A/B runs)
+    const bool sep = K >= acc_min_k;
+    if (c.cout % 128 == 0) {
+        if (!sep) return launch_f16<128, 1, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+        if (nslot == 2) return launch_f16<128, 3, 2, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+        return launch_f16<128, 2, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+    }
+    if (!sep) return launch_f16<64, 1, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+    if (nslot == 2) return launch_f16<64, 3, 2, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+    return launch_f16<64, 3, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+}
+
 static int run_conv_bf16(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
                          cudaStream_t st) {
-    const int K = c.k * c.k * c.cin;
-    static const int wide_min_k = getenv("IRN_BF_WIDE_MINK") ? atoi(getenv("IRN_BF_WIDE_MINK")) : 512;
-    // one accumulator per tile: on B200 separate accumulators for the hi*hi and the cross terms (NACC = 2, 3) change nothing
-    // measurable (tools/bf16_bringup.py, profiles/r02_conv_bf16x3_vs_f16x3.md) and cost TMEM / the epilogue overlap
-    if (c.cout % 256 == 0 && K >= wide_min_k && !residual) return launch_bf16<256, 1>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
-    if (c.cout % 128 == 0) return launch_bf16<128, 1>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
-    return launch_bf16<64, 1>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+    static const int use_halo = getenv("IRN_F16_HALO") ? atoi(getenv("IRN_F16_HALO")) : 1;
+    if (use_halo && c.k == 3 && c.stride == 1 && c.pad == 1) return dispatch_f16<true>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+    return dispatch_f16<false>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
 }
 
 static int run_conv(const irn_net* net, const Conv& c, const float* in, int B, int H, int W, const float* residual, float* out, bool relu,

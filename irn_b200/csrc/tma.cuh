@@ -82,6 +82,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (spin > (1u << 26)) __trap();
 }
 
+// Non-suspending poll (mbarrier.test_wait returns at once): for waits on the per-k-block critical path, where the wake-up latency
+// of a suspended try_wait (~1 us measured around the A-slot ring of the f16x3 kernels) would be paid every trip.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_test_wait(bar, parity); ++spin)
+        if (spin > (1u << 28)) __trap();
+}
+
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
