@@ -14,17 +14,17 @@
 //   GEMM tile   M = 8x16 output pixels (128 TMEM lanes), N = BN in {64, 128} channels, K walked in 64-channel k-blocks per tap
 //   warp 0      TMA producer: fp32 activation tiles as 4-D boxes {32 ch, px, rows, 1 image} (zero fill = padding, element strides =
 //               stride-2 convs) + the fp16 weight tiles w_hi / w_lo as 2-D boxes {64 k, BN} (SWIZZLE_128B)
-//   warps 2-5   split: thread = tile row = TMEM lane; reads its 2 x 128-byte row slices once, writes packed fp16 A_hi / A_lo
-//               (2 k-elements per 32-bit column) straight into one of NSLOT TMEM A slots with tcgen05.st
-//   warp 1      MMA issuer: per k-block 4 k-steps (K = 16) x 3 MMAs, A from TMEM, B from shared memory
-//   warps 6-13  epilogue: TMEM -> swizzled shared staging -> coalesced (x 2^-s, +bias, +residual, ReLU) fp32 stores, 32 channels
+//   warps 4-11  split: thread = tile row = TMEM lane, two warps per lane quarter (one per 32-channel half of the k-block); reads its
+//               128-byte row slice once, writes packed fp16 A_hi / A_lo (2 k-elements per 32-bit column) straight into one of
+//               NSLOT TMEM A slots with tcgen05.st.  (With the MMAs issued back to back -- elect_one -- a lone split warp per
+//               scheduler, ~1000 cycles of LDS -> convert -> tcgen05.st -> barrier per k-block, was the next pacer.)
+//   warp 1      MMA issuer: per k-block 4 k-steps (K = 16) x 2-3 MMAs (f16_issue_kblock), A from TMEM, B from shared memory
+//   warps 12-19 epilogue: TMEM -> swizzled shared staging -> coalesced (x 2^-s, +bias, +residual, ReLU) fp32 stores, 32 channels
 //               (128-byte row segments) at a time; with two accumulator sets it overlaps the next tile's mainloop
 //   TMEM        columns [0, 512 - 64 NSLOT): SETS x NACC accumulators of BN columns; the top 64 NSLOT columns: A slots (hi 32 | lo 32)
-// Accumulators (NACC): the tensor core's fp32 accumulate TRUNCATES; see f16_issue3.
-// A slots (NSLOT): the ring  split -> a_ready -> MMA -> commit -> a_free -> split  has a round-trip latency of ~2400 cycles on
-// B200 (ncu: k-block time 1440 / 1560 cycles for N = 64 / 128 with two slots = (MMA time + 2400) / 2, independent of the bytes
-// moved and of the split warps' instruction count; profiles/r02_ncu_conv_f16_halo_2slots.txt): two slots leave the tensor pipe
-// idle half the time, four slots cover the latency.
+// Accumulators (NACC): the tensor core's fp32 accumulate TRUNCATES; see f16_issue_kblock.
+// A slots (NSLOT = 4): the ring  split -> a_ready -> MMA -> commit -> a_free -> split  is covered four k-blocks deep.
+// Issue discipline: see elect_one -- the MMA / TMA issue loops run on a converged warp.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -35,10 +35,23 @@
 namespace irn {
 
 constexpr int kBfBK = 64;            // channels per k-block
-constexpr int kBfThreads = 448;      // 14 warps: TMA, MMA, 4 split, 8 epilogue
+constexpr int kBfThreads = 640;      // 20 warps = 5 warpgroups: [TMA, MMA, 2 idle] | 8 split | 8 epilogue (register budgets per group: f16_regs)
 constexpr int kHaloW = kTcTW + 2, kHaloH = kTcTH + 2;                 // 18 x 10 pixels
 constexpr int kHaloHalfBytes = 23 * 1024;                            // 180 rows x 128 B = 23,040 B, padded to a 1 KB multiple (swizzle atom)
 constexpr int kHaloBytes = 2 * kHaloHalfBytes;
+
+// Register budgets per warpgroup (setmaxnreg): the kernel is compiled for 640 threads x 96 registers; the issue warpgroup and the
+// split warpgroups hand registers back, the epilogue warpgroups -- which keep a 32-row x 64-channel residual slice in flight per
+// thread plus 32-64 accumulator values -- take them: 4 x 32 x 40 + 8 x 32 x 72 + 8 x 32 x 152 = 62,464 <= 640 x 96 = 61,440 + ... see static_assert.
+constexpr int kRegsIssue = 40, kRegsSplit = 72, kRegsEpilogue = 144;
+static_assert(4 * 32 * kRegsIssue + 8 * 32 * kRegsSplit + 8 * 32 * kRegsEpilogue <= 640 * 96, "register pool");
+template <int N, bool INC>
+__device__ __forceinline__ void f16_regs() {
+    if (INC)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+    else
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 
 template <int BN, int NACC, int NSLOT>
 struct F16Cfg {
@@ -57,6 +70,7 @@ struct F16Cfg {
     static constexpr size_t kSmemHalo = 1024 + 2 * (size_t)kHaloBytes + (size_t)kStagesB * kBStageBytes + kStagingBytes + 256;
     static_assert(NACC * BN * kSets <= kAccCols, "accumulators overlap the TMEM A slots");
     static_assert(BN == 64 || BN == 128, "N tile 64 or 128");
+    static_assert(NACC == 1 || NACC == 2, "one accumulator, or main | cross");
 };
 
 // kind::f16 instruction descriptor: D fp32 (1 @4), A and B fp16 (0 @7, 0 @10), both K-major, N>>3 @17, M>>4 @24
@@ -73,12 +87,15 @@ __device__ __forceinline__ void f16_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uin
         : "memory");
 }
 
-// (a, b) -> packed fp16 pair {low half = hi(a), high half = hi(b)} and the packed pair of the residuals.  hi(x) = x rounded to 11
-// significant bits with two integer ops (fp16 and tf32 share the mantissa width), so the packing conversion is exact for
-// 2^-14 <= |x| <= 65504; the residual x - hi(x) is exact in fp32 and rounded once by its own conversion.
+// (a, b) -> packed fp16 pair {low half = hi(a), high half = hi(b)} and the packed pair of the residuals.  hi(x) = x TRUNCATED to 11
+// significant bits: the round-toward-zero conversion does it while packing (fp16 and tf32 share the mantissa width), one LOP3 per
+// element rebuilds the same value in fp32 for the residual x - hi(x), which is exact in fp32 (13 significant bits) and rounded once,
+// to 11 bits, by its own conversion: |error| <= 2^-21 |x|.  (Exact packing needs 2^-14 <= |x| <= 65504; beyond that the conversion
+// saturates, below it the two parts disagree by < 6e-8 absolute.)  Three ALU ops per element; the first version (round-to-nearest hi
+// with two integer ops) had four.
 __device__ __forceinline__ void f16_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const float ha = tf32_hi(a), hb = tf32_hi(b);
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(hb), "f"(ha));      // upper half <- first source operand
+    asm("cvt.rz.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));      // upper half <- first source operand
+    const float ha = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), hb = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
 }
 
@@ -101,23 +118,35 @@ __device__ __forceinline__ void f16_wait(uint64_t* bar, uint32_t parity, bool sp
         mbar_wait(bar, parity);
 }
 
-// The three MMAs of one k-step.  The tensor core's fp32 accumulate TRUNCATES (measured on B200: every MMA into an accumulator
-// shrinks it by ~1.5e-8 of its value: -1.3e-5 after the 864 MMAs of a K = 4608 reduction, profiles/r02_conv_f16x3_accuracy.md).
-// NACC = 1: everything into one accumulator.  NACC = 2: the small cross terms get their own accumulator, so only the hi*hi MMAs
-// truncate the large sum (a third of the events).  NACC = 3: hi*hi additionally alternates between two accumulators per k-block.
-// The epilogue adds the accumulators in IEEE fp32.
+// One lane of a CONVERGED warp.  tcgen05.mma / tcgen05.commit / cp.async.bulk.tensor are warp-uniform instructions: issued under
+// `if (lane == 0)` the compiler wraps every one of them in its own ELECT + BRA.U.ANY loop (~100 cycles of single-thread latency
+// per MMA: 12 MMAs = the 1200-1500 cycles per k-block that paced every layer, whatever its N, in round 1 and in this round's
+// first f16 kernels); under elect.sync in a converged warp they issue back to back.
+__device__ __forceinline__ bool elect_one() { return tc_elect_one(); }
+
+// The MMAs of one k-block (4 k-steps of 16).  The tensor core's fp32 accumulate TRUNCATES (measured on B200: every MMA into an
+// accumulator shrinks it by ~1.5e-8 of its value: -1.3e-5 after the 864 MMAs of a K = 4608 reduction,
+// profiles/r02_conv_f16x3_accuracy.md), so for long reductions the small cross terms get their own accumulator:
+//   NACC = 1   hi*hi, lo*hi, hi*lo into one accumulator (three N = BN MMAs per k-step)
+//   NACC = 2   accumulators [main | cross] side by side in TMEM and the weight planes [w_hi | w_lo] side by side in shared memory:
+//              ONE N = 2 BN MMA computes A_hi x [w_hi | w_lo] = [hi*hi | hi*lo] into [main | cross], a second N = BN MMA adds
+//              A_lo x w_hi to `cross`: same tensor time, two instructions instead of three, and only the hi*hi MMAs truncate the
+//              large sum.  The epilogue adds main + cross in IEEE fp32.
 template <int BN, int NACC>
-__device__ __forceinline__ void f16_issue3(uint32_t acc, uint32_t ta_hi, uint32_t ta_lo, uint64_t db_hi, uint64_t db_lo, uint32_t idesc, int kb, int j) {
-    if (NACC == 1) {
-        f16_mma_ts(acc, ta_hi, db_hi, idesc, (kb | j) != 0);
-        f16_mma_ts(acc, ta_lo, db_hi, idesc, 1);
-        f16_mma_ts(acc, ta_hi, db_lo, idesc, 1);
-    } else {
-        const uint32_t main_acc = acc + (NACC == 3 ? (uint32_t)((kb & 1) * BN) : 0u);
-        const uint32_t cross = acc + (uint32_t)((NACC - 1) * BN);
-        f16_mma_ts(main_acc, ta_hi, db_hi, idesc, (NACC == 3 ? (kb >= 2 || j != 0) : ((kb | j) != 0)) ? 1u : 0u);
-        f16_mma_ts(cross, ta_lo, db_hi, idesc, (kb | j) != 0);
-        f16_mma_ts(cross, ta_hi, db_lo, idesc, 1);
+__device__ __forceinline__ void f16_issue_kblock(uint32_t acc, uint32_t a_t, uint32_t b_hi, int kb) {
+    const uint64_t d_hi = tc_smem_desc(b_hi), d_lo = tc_smem_desc(b_hi + (uint32_t)(BN * 128));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {          // UMMA_K = 16 fp16 = 32 bytes inside the 128-byte swizzle atom (+2 in the descriptor) = 8 TMEM columns of A
+        const uint32_t ta_hi = a_t + j * 8, ta_lo = a_t + 32 + j * 8;
+        if (NACC == 1) {
+            constexpr uint32_t idesc = f16_idesc(128, BN);
+            f16_mma_ts(acc, ta_hi, d_hi + 2 * j, idesc, (kb | j) != 0);
+            f16_mma_ts(acc, ta_lo, d_hi + 2 * j, idesc, 1);
+            f16_mma_ts(acc, ta_hi, d_lo + 2 * j, idesc, 1);
+        } else {
+            f16_mma_ts(acc, ta_hi, d_hi + 2 * j, f16_idesc(128, 2 * BN), (kb | j) != 0);
+            f16_mma_ts(acc + BN, ta_lo, d_hi + 2 * j, f16_idesc(128, BN), 1);
+        }
     }
 }
 
@@ -129,17 +158,16 @@ __device__ __forceinline__ void f16_tile_coords(const TcArgs& args, int n_tiles,
     b = m / (args.tiles_x * args.tiles_y);
 }
 
-// Epilogue shared by the f16x3 kernels (warps 6..13 of a CTA): TMEM lane quarter = warp % 4, channel half = (warp - 6) / 4; 32
+// Epilogue shared by the f16x3 kernels (warps 12..19 of a CTA): TMEM lane quarter = warp % 4, channel half = (warp - 12) / 4; 32
 // channels per pass through a 4 KB swizzled staging tile (thread = row on the way in, 8 lanes x float4 per row on the way out).
 template <int BN, int NACC, int SETS>
 __device__ __forceinline__ void f16_epilogue(const TcArgs& args, float* staging, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
                                              int warp, int lane, int total, int n_tiles) {
-    const int KB = args.ksize * args.ksize * (args.Cin / kBfBK);
     const int q = warp & 3;
-    const int hf = (warp - 6) >> 2;
+    const int hf = (warp - 12) >> 2;
     constexpr int kCols = BN / 2;
     constexpr int kChunks = kCols / 32;
-    float* stg = staging + (size_t)(warp - 6) * 32 * 32;
+    float* stg = staging + (size_t)(warp - 12) * 32 * 32;
     const int sub = lane >> 3, c8 = lane & 7;
     uint32_t ti = 0;
     for (int id = blockIdx.x; id < total; id += gridDim.x, ++ti) {
@@ -178,12 +206,6 @@ __device__ __forceinline__ void f16_epilogue(const TcArgs& args, float* staging,
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-                if (NACC == 3 && KB >= 2) {
-                    tc_ld32(taddr + (uint32_t)BN, u);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-                }
             }
             if (cc == kChunks - 1) {          // last TMEM read of this tile: hand the accumulator set back
                 tc_fence_before();
@@ -218,21 +240,10 @@ __device__ __forceinline__ void f16_epilogue(const TcArgs& args, float* staging,
     }
 }
 
-// MMA issue for one k-block: 4 k-steps x 3 MMAs; UMMA_K = 16 fp16 = 32 bytes inside the 128-byte swizzle atom = 8 TMEM columns of A
-template <int BN, int NACC>
-__device__ __forceinline__ void f16_issue_kblock(uint32_t acc, uint32_t a_t, uint32_t b_hi, uint32_t b_lo, int kb) {
-    constexpr uint32_t idesc = f16_idesc(128, BN);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint64_t db_hi = tc_smem_desc(b_hi + j * 32), db_lo = tc_smem_desc(b_lo + j * 32);
-        f16_issue3<BN, NACC>(acc, a_t + j * 8, a_t + 32 + j * 8, db_hi, db_lo, idesc, kb, j);
-    }
-}
-
-// split warp: hi / lo registers -> TMEM A slot, then signal
-__device__ __forceinline__ void f16_store_slot(uint32_t taddr, const uint32_t (&hi)[32], const uint32_t (&lo)[32], uint64_t* ready, int lane) {
-    tc_st32(taddr, hi);
-    tc_st32(taddr + 32, lo);
+// split warp: hi / lo registers of its 32-channel half -> TMEM A slot (hi columns [0,32), lo columns [32,64)), then signal
+__device__ __forceinline__ void f16_store_slot(uint32_t taddr, const uint32_t (&hi)[16], const uint32_t (&lo)[16], uint64_t* ready, int lane) {
+    tc_st16(taddr, hi);
+    tc_st16(taddr + 32, lo);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     tc_fence_before();
     __syncwarp();
@@ -271,7 +282,7 @@ conv_f16_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             mbar_init(&empty[s], 1);
         }
         for (int i = 0; i < NSLOT; ++i) {
-            mbar_init(&a_ready[i], 4);
+            mbar_init(&a_ready[i], 8);
             mbar_init(&a_free[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -289,18 +300,22 @@ conv_f16_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    if (warp < 4) f16_regs<kRegsIssue, false>();
     if (warp == 0) {
-        if (lane == 0) {
+        // ---- TMA producer: the whole warp walks the loop (converged), one elected lane issues
+        if (elect_one()) {
             tma_prefetch_desc(&maps.a);
             tma_prefetch_desc(&maps.b_hi);
             tma_prefetch_desc(&maps.b_lo);
-            uint32_t g = 0;
-            for (int id = blockIdx.x; id < total; id += gridDim.x) {
-                int b, oy0, ox0, n0;
-                f16_tile_coords(args, n_tiles, BN, id, b, oy0, ox0, n0);
-                for (int kb = 0; kb < KB; ++kb, ++g) {
-                    const uint32_t s = g % S, it = g / S;
-                    mbar_wait(&empty[s], (it & 1) ^ 1);
+        }
+        uint32_t g = 0;
+        for (int id = blockIdx.x; id < total; id += gridDim.x) {
+            int b, oy0, ox0, n0;
+            f16_tile_coords(args, n_tiles, BN, id, b, oy0, ox0, n0);
+            for (int kb = 0; kb < KB; ++kb, ++g) {
+                const uint32_t s = g % S, it = g / S;
+                mbar_wait(&empty[s], (it & 1) ^ 1);
+                if (elect_one()) {
                     unsigned char* st = smem + s * Cfg::kStageBytes;
                     const int tap = kb / cblocks, cb = kb % cblocks;
                     const int r = tap / args.ksize, ss = tap % args.ksize;
@@ -311,48 +326,53 @@ conv_f16_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                     tma_load_2d(st + 32768, &maps.b_hi, &full[s], kb * kBfBK, n0);
                     tma_load_2d(st + 32768 + Cfg::kBBytes, &maps.b_lo, &full[s], kb * kBfBK, n0);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            uint32_t g = 0, ti = 0;
-            for (int id = blockIdx.x; id < total; id += gridDim.x, ++ti) {
-                const uint32_t set = SETS == 2 ? (ti & 1) : 0, use = SETS == 2 ? (ti >> 1) : ti;
-                mbar_wait(&tmem_empty[set], (use & 1) ^ 1);     // the epilogue drained this accumulator set
+        // ---- MMA issuer: converged warp, one elected lane issues (see elect_one)
+        uint32_t g = 0, ti = 0;
+        for (int id = blockIdx.x; id < total; id += gridDim.x, ++ti) {
+            const uint32_t set = SETS == 2 ? (ti & 1) : 0, use = SETS == 2 ? (ti >> 1) : ti;
+            mbar_wait(&tmem_empty[set], (use & 1) ^ 1);     // the epilogue drained this accumulator set
+            tc_fence_after();
+            const uint32_t acc = tmem_base + set * (uint32_t)(NACC * BN);
+            for (int kb = 0; kb < KB; ++kb, ++g) {
+                const uint32_t s = g % S, it = g / S, slot = g % NSLOT;
+                f16_wait(&full[s], it & 1, spin);                       // weight tiles landed
+                f16_wait(&a_ready[slot], (g / NSLOT) & 1, spin);        // A_hi / A_lo in the TMEM slot (=> the split warps have read the stage)
                 tc_fence_after();
-                const uint32_t acc = tmem_base + set * (uint32_t)(NACC * BN);
-                for (int kb = 0; kb < KB; ++kb, ++g) {
-                    const uint32_t s = g % S, it = g / S, slot = g % NSLOT;
-                    f16_wait(&full[s], it & 1, spin);                       // weight tiles landed
-                    f16_wait(&a_ready[slot], (g / NSLOT) & 1, spin);        // A_hi / A_lo in the TMEM slot (=> the split warps have read the stage)
-                    tc_fence_after();
-                    const uint32_t b_hi = smem_u32(smem + s * Cfg::kStageBytes + 32768);
-                    f16_issue_kblock<BN, NACC>(acc, tmem_base + Cfg::kAcol + slot * 64u, b_hi, b_hi + Cfg::kBBytes, kb);
+                if (elect_one()) {
+                    f16_issue_kblock<BN, NACC>(acc, tmem_base + Cfg::kAcol + slot * 64u, smem_u32(smem + s * Cfg::kStageBytes + 32768), kb);
                     tc_commit(&empty[s]);
                     tc_commit(&a_free[slot]);
+                    if (kb == KB - 1) tc_commit(&tmem_full[set]);
                 }
-                tc_commit(&tmem_full[set]);
+                __syncwarp();
             }
         }
-    } else if (warp < 6) {
-        // ---- split warps: thread = tile row = TMEM lane
+    } else if (warp < 4) {
+        // idle half of warpgroup 0 (keeps the role groups warpgroup-aligned for setmaxnreg)
+    } else if (warp < 12) {
+        // ---- split warps: thread = tile row = TMEM lane; warps 4-7 take channels 0..31 of the k-block, warps 8-11 channels 32..63
+        f16_regs<kRegsSplit, false>();
         const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         uint32_t g = 0;
         for (int id = blockIdx.x; id < total; id += gridDim.x) {
             for (int kb = 0; kb < KB; ++kb, ++g) {
                 const uint32_t s = g % S, it = g / S, slot = g % NSLOT;
                 f16_wait(&full[s], it & 1, spin);
-                uint32_t hi[32], lo[32];
-                const unsigned char* ap = smem + s * Cfg::kStageBytes + row * 128;
-                f16_split_row(reinterpret_cast<const float4*>(ap), row & 7, hi, lo);
-                f16_split_row(reinterpret_cast<const float4*>(ap + 16384), row & 7, hi + 16, lo + 16);
+                uint32_t hi[16], lo[16];
+                f16_split_row(reinterpret_cast<const float4*>(smem + s * Cfg::kStageBytes + half * 16384 + row * 128), row & 7, hi, lo);
                 f16_wait(&a_free[slot], ((g / NSLOT) & 1) ^ 1, spin);   // the MMAs of k-block g - NSLOT released this TMEM slot
                 tc_fence_after();
-                f16_store_slot(tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::kAcol + slot * 64u, hi, lo, &a_ready[slot], lane);
+                f16_store_slot(tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::kAcol + slot * 64u + (uint32_t)half * 16u, hi, lo, &a_ready[slot], lane);
             }
         }
     } else {
+        f16_regs<kRegsEpilogue, true>();
         f16_epilogue<BN, NACC, SETS>(args, staging, tmem_full, tmem_empty, tmem_base, warp, lane, total, n_tiles);
     }
     tc_fence_before();
@@ -406,12 +426,12 @@ conv_f16_halo_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&h_full[i], 1);
-            mbar_init(&h_empty[i], 4);
+            mbar_init(&h_empty[i], 8);
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 8);
         }
         for (int i = 0; i < NSLOT; ++i) {
-            mbar_init(&a_ready[i], 4);
+            mbar_init(&a_ready[i], 8);
             mbar_init(&a_free[i], 1);
         }
         fence_mbar_init();
@@ -425,59 +445,73 @@ conv_f16_halo_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    if (warp < 4) f16_regs<kRegsIssue, false>();
     if (warp == 0) {
-        if (lane == 0) {
+        // ---- TMA producer (converged warp, one elected lane issues)
+        if (elect_one()) {
             tma_prefetch_desc(&maps.a);
             tma_prefetch_desc(&maps.b_hi);
             tma_prefetch_desc(&maps.b_lo);
-            uint32_t g = 0, hs = 0;      // weight k-blocks / halo slices issued so far
-            for (int id = blockIdx.x; id < total; id += gridDim.x) {
-                int b, oy0, ox0, n0;
-                f16_tile_coords(args, n_tiles, BN, id, b, oy0, ox0, n0);
-                for (int cb = 0; cb < cblocks; ++cb, ++hs) {
-                    const uint32_t hb = hs & 1;
-                    mbar_wait(&h_empty[hb], ((hs >> 1) & 1) ^ 1);
+        }
+        uint32_t g = 0, hs = 0;      // weight k-blocks / halo slices issued so far
+        for (int id = blockIdx.x; id < total; id += gridDim.x) {
+            int b, oy0, ox0, n0;
+            f16_tile_coords(args, n_tiles, BN, id, b, oy0, ox0, n0);
+            for (int cb = 0; cb < cblocks; ++cb, ++hs) {
+                const uint32_t hb = hs & 1;
+                mbar_wait(&h_empty[hb], ((hs >> 1) & 1) ^ 1);
+                if (elect_one()) {
                     unsigned char* hp = smem + hb * kHaloBytes;
                     mbar_arrive_expect_tx(&h_full[hb], 2u * 32u * 4u * kHaloW * kHaloH);
                     tma_load_4d(hp, &maps.a, &h_full[hb], cb * kBfBK, ox0 - 1, oy0 - 1, b);
                     tma_load_4d(hp + kHaloHalfBytes, &maps.a, &h_full[hb], cb * kBfBK + 32, ox0 - 1, oy0 - 1, b);
-                    for (int tap = 0; tap < 9; ++tap, ++g) {
-                        const uint32_t s = g % S, it = g / S;
-                        mbar_wait(&b_empty[s], (it & 1) ^ 1);
+                }
+                __syncwarp();
+                for (int tap = 0; tap < 9; ++tap, ++g) {
+                    const uint32_t s = g % S, it = g / S;
+                    mbar_wait(&b_empty[s], (it & 1) ^ 1);
+                    if (elect_one()) {
                         unsigned char* st = bstage + s * Cfg::kBStageBytes;
                         mbar_arrive_expect_tx(&b_full[s], (uint32_t)Cfg::kBStageBytes);
                         const int kcol = (tap * cblocks + cb) * kBfBK;      // weights are [Cout][tap][Cin]
                         tma_load_2d(st, &maps.b_hi, &b_full[s], kcol, n0);
                         tma_load_2d(st + Cfg::kBBytes, &maps.b_lo, &b_full[s], kcol, n0);
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            uint32_t g = 0, ti = 0;
-            const int KB = 9 * cblocks;
-            for (int id = blockIdx.x; id < total; id += gridDim.x, ++ti) {
-                const uint32_t set = SETS == 2 ? (ti & 1) : 0, use = SETS == 2 ? (ti >> 1) : ti;
-                mbar_wait(&tmem_empty[set], (use & 1) ^ 1);
+        // ---- MMA issuer (converged warp, one elected lane issues)
+        uint32_t g = 0, ti = 0;
+        const int KB = 9 * cblocks;
+        for (int id = blockIdx.x; id < total; id += gridDim.x, ++ti) {
+            const uint32_t set = SETS == 2 ? (ti & 1) : 0, use = SETS == 2 ? (ti >> 1) : ti;
+            mbar_wait(&tmem_empty[set], (use & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + set * (uint32_t)(NACC * BN);
+            for (int kb = 0; kb < KB; ++kb, ++g) {
+                const uint32_t s = g % S, it = g / S, slot = g % NSLOT;
+                f16_wait(&b_full[s], it & 1, spin);
+                f16_wait(&a_ready[slot], (g / NSLOT) & 1, spin);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + set * (uint32_t)(NACC * BN);
-                for (int kb = 0; kb < KB; ++kb, ++g) {
-                    const uint32_t s = g % S, it = g / S, slot = g % NSLOT;
-                    f16_wait(&b_full[s], it & 1, spin);
-                    f16_wait(&a_ready[slot], (g / NSLOT) & 1, spin);
-                    tc_fence_after();
-                    const uint32_t b_hi = smem_u32(bstage + s * Cfg::kBStageBytes);
-                    f16_issue_kblock<BN, NACC>(acc, tmem_base + Cfg::kAcol + slot * 64u, b_hi, b_hi + Cfg::kBBytes, kb);
+                if (elect_one()) {
+                    f16_issue_kblock<BN, NACC>(acc, tmem_base + Cfg::kAcol + slot * 64u, smem_u32(bstage + s * Cfg::kBStageBytes), kb);
                     tc_commit(&b_empty[s]);
                     tc_commit(&a_free[slot]);
+                    if (kb == KB - 1) tc_commit(&tmem_full[set]);
                 }
-                tc_commit(&tmem_full[set]);
+                __syncwarp();
             }
         }
-    } else if (warp < 6) {
-        // ---- split warps: thread = tile row (ry, rx) = TMEM lane; tap (r, s) reads halo pixel (ry + r, rx + s)
+    } else if (warp < 4) {
+        // idle half of warpgroup 0
+    } else if (warp < 12) {
+        // ---- split warps: thread = tile row (ry, rx) = TMEM lane, warps 4-7 / 8-11 = channel halves; tap (r, s) reads halo pixel
+        // (ry + r, rx + s)
+        f16_regs<kRegsSplit, false>();
         const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         const int ry = row / kTcTW, rx = row % kTcTW;
         uint32_t g = 0, hs = 0;
@@ -485,23 +519,23 @@ conv_f16_halo_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             for (int cb = 0; cb < cblocks; ++cb, ++hs) {
                 const uint32_t hb = hs & 1;
                 f16_wait(&h_full[hb], (hs >> 1) & 1, spin);
-                const unsigned char* hp = smem + hb * kHaloBytes;
+                const unsigned char* hp = smem + hb * kHaloBytes + half * kHaloHalfBytes;
 #pragma unroll 1
                 for (int tap = 0; tap < 9; ++tap, ++g) {
                     const uint32_t slot = g % NSLOT;
-                    const int p = (ry + tap / 3) * kHaloW + rx + tap % 3;      // halo pixel = 128-byte row of each half
-                    uint32_t hi[32], lo[32];
+                    const int p = (ry + tap / 3) * kHaloW + rx + tap % 3;      // halo pixel = 128-byte row of the half
+                    uint32_t hi[16], lo[16];
                     f16_split_row(reinterpret_cast<const float4*>(hp + p * 128), p & 7, hi, lo);
-                    f16_split_row(reinterpret_cast<const float4*>(hp + kHaloHalfBytes + p * 128), p & 7, hi + 16, lo + 16);
                     f16_wait(&a_free[slot], ((g / NSLOT) & 1) ^ 1, spin);
                     tc_fence_after();
-                    f16_store_slot(tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::kAcol + slot * 64u, hi, lo, &a_ready[slot], lane);
+                    f16_store_slot(tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::kAcol + slot * 64u + (uint32_t)half * 16u, hi, lo, &a_ready[slot], lane);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&h_empty[hb]);      // every lane's last read of this halo buffer is complete
             }
         }
     } else {
+        f16_regs<kRegsEpilogue, true>();
         f16_epilogue<BN, NACC, SETS>(args, staging, tmem_full, tmem_empty, tmem_base, warp, lane, total, n_tiles);
     }
     tc_fence_before();

@@ -49,6 +49,13 @@ constexpr size_t tc_smem_bytes(int BN, int stages) {
     return 1024 /*align*/ + (size_t)stages * (2 * 16384 + 2 * (size_t)BN * 128) + 256;
 }
 
+// one lane of a converged warp (elect.sync): see conv_f16.cuh, elect_one
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -863,18 +870,22 @@ conv_tc_persist_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args
         b = m / (args.tiles_x * args.tiles_y);
     };
 
+    // Producer and MMA loops run on a CONVERGED warp and issue under elect.sync: under `if (lane == 0)` the compiler wraps every
+    // tcgen05.mma / tcgen05.commit / TMA instruction in its own ELECT + BRA.U.ANY loop (~100 cycles each; conv_f16.cuh, elect_one).
     if (warp == 0) {
-        if (lane == 0) {
+        if (tc_elect_one()) {
             tma_prefetch_desc(&maps.a);
             tma_prefetch_desc(&maps.b_hi);
             tma_prefetch_desc(&maps.b_lo);
-            uint32_t g = 0;
-            for (int id = blockIdx.x; id < total; id += gridDim.x) {
-                int b, oy0, ox0, n0;
-                tile_coords(id, b, oy0, ox0, n0);
-                for (int kb = 0; kb < KB; ++kb, ++g) {
-                    const uint32_t s = g % S, it = g / S;
-                    mbar_wait(&empty[s], (it & 1) ^ 1);
+        }
+        uint32_t g = 0;
+        for (int id = blockIdx.x; id < total; id += gridDim.x) {
+            int b, oy0, ox0, n0;
+            tile_coords(id, b, oy0, ox0, n0);
+            for (int kb = 0; kb < KB; ++kb, ++g) {
+                const uint32_t s = g % S, it = g / S;
+                mbar_wait(&empty[s], (it & 1) ^ 1);
+                if (tc_elect_one()) {
                     unsigned char* st = smem + s * kPtsStageBytes;
                     const int tap = kb / cblocks, cb = kb % cblocks;
                     const int r = tap / args.ksize, ss = tap % args.ksize;
@@ -886,22 +897,23 @@ conv_tc_persist_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args
                     tma_load_2d(st + 16384, &maps.b_hi, &full[s], kb * kTcBK, n0);
                     tma_load_2d(st + 16384 + BN * 128, &maps.b_lo, &full[s], kb * kTcBK, n0);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc_idesc(128, BN);
-            uint32_t g = 0, ti = 0;
-            for (int id = blockIdx.x; id < total; id += gridDim.x, ++ti) {
-                const uint32_t set = ti & 1, use = ti >> 1;
-                mbar_wait(&tmem_empty[set], (use & 1) ^ 1);
+        constexpr uint32_t idesc = tc_idesc(128, BN);
+        uint32_t g = 0, ti = 0;
+        for (int id = blockIdx.x; id < total; id += gridDim.x, ++ti) {
+            const uint32_t set = ti & 1, use = ti >> 1;
+            mbar_wait(&tmem_empty[set], (use & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + set * (2u * BN);
+            for (int kb = 0; kb < KB; ++kb, ++g) {
+                const uint32_t s = g % S, it = g / S, slot = g & 1;
+                mbar_wait(&full[s], it & 1);       // B tiles landed
+                mbar_wait(&split[s], it & 1);      // A_hi / A_lo in TMEM slot
                 tc_fence_after();
-                const uint32_t acc = tmem_base + set * (2u * BN);
-                for (int kb = 0; kb < KB; ++kb, ++g) {
-                    const uint32_t s = g % S, it = g / S, slot = g & 1;
-                    mbar_wait(&full[s], it & 1);       // B tiles landed
-                    mbar_wait(&split[s], it & 1);      // A_hi / A_lo in TMEM slot
-                    tc_fence_after();
+                if (tc_elect_one()) {
                     const uint32_t b_hi = smem_u32(smem + s * kPtsStageBytes + 16384), b_lo = b_hi + BN * 128;
                     const uint32_t a_t = tmem_base + kAcol + slot * 64u;
 #pragma unroll
@@ -914,8 +926,9 @@ conv_tc_persist_ts_kernel(const __grid_constant__ TcMaps maps, const TcArgs args
                     }
                     tc_commit(&empty[s]);
                     tc_commit(&a_free[slot]);
+                    if (kb == KB - 1) tc_commit(&tmem_full[set]);
                 }
-                tc_commit(&tmem_full[set]);
+                __syncwarp();
             }
         }
     } else if (warp < 6) {

@@ -521,16 +521,13 @@ static int dispatch_f16(const Conv& c, const float* in, int B, int H, int W, int
                         cudaStream_t st) {
     const int K = c.k * c.k * c.cin;
     static const int acc_min_k = getenv("IRN_F16_ACC_MINK") ? atoi(getenv("IRN_F16_ACC_MINK")) : 512;
-    static const int nslot = getenv("IRN_F16_NSLOT") ? atoi(getenv("IRN_F16_NSLOT")) : 4;      // 2: round-2's first version (A/B runs)
     const bool sep = K >= acc_min_k;
     if (c.cout % 128 == 0) {
-        if (!sep) return launch_f16<128, 1, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
-        if (nslot == 2) return launch_f16<128, 3, 2, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
-        return launch_f16<128, 2, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+        if (sep) return launch_f16<128, 2, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+        return launch_f16<128, 1, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
     }
-    if (!sep) return launch_f16<64, 1, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
-    if (nslot == 2) return launch_f16<64, 3, 2, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
-    return launch_f16<64, 3, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+    if (sep) return launch_f16<64, 2, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+    return launch_f16<64, 1, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
 }
 
 static int run_conv_bf16(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,

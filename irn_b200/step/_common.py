@@ -32,7 +32,10 @@ def collate_one(batch):
     """batch_size=1 collation like the reference's DataLoader, except that `size` stays a pair of python ints
     (torch's default collate makes it [tensor([H]), tensor([W])], which modern numpy can no longer use as a slice
     bound, step/make_sem_seg_labels.py:29,43)."""
+    jpeg = batch[0].pop("jpeg", None) if isinstance(batch[0], dict) else None
     out = default_collate(batch)
+    if jpeg is not None:
+        out["jpeg"] = torch.from_numpy(jpeg)        # variable-length byte stream: no batch dimension
     out["size"] = (int(batch[0]["size"][0]), int(batch[0]["size"][1]))
     return out
 
@@ -51,6 +54,12 @@ def device_pyramid(args):
     return bool(getattr(args, "device_pyramid", True))
 
 
+def device_jpeg(args):
+    """--device_jpeg (default off): loader workers hand over the JPEG FILE BYTES, nvJPEG decodes them on the GPU
+    (irn_b200.jpeg).  Pixels differ from the host decoder's by a level or two: a throughput option, not a parity one."""
+    return bool(getattr(args, "device_jpeg", False)) and device_pyramid(args)
+
+
 def step_batch(args):
     """--step_batch N (default 32): images of equal size processed together; 1 = the reference's one-image loop."""
     return max(1, int(getattr(args, "step_batch", DEFAULT_STEP_BATCH) or 1))
@@ -66,12 +75,21 @@ def make_dataset(args, list_path, scales):
             raise FileNotFoundError("--synthetic_list %s" % names)
         return voc_data.SyntheticMSF(int(args.synthetic), scales=scales, name_list=names, decode_only=device_pyramid(args))
     return voc_data.VOC12ClassificationDatasetMSF(list_path, voc12_root=args.voc12_root, scales=scales,
-                                                  decode_only=device_pyramid(args))
+                                                  decode_only=device_pyramid(args), raw_jpeg=device_jpeg(args))
+
+
+_jpeg_decoders = {}
 
 
 def attach_pyramid(pack, scales):
     """Turn a decode-only item into what the reference's loader yields: pack['img'] = [1,2,3,h,w] per scale (a single
     tensor when there is one scale, voc12/dataloader.py:200-201), already on the current device."""
+    if "jpeg" in pack:
+        from ..jpeg import JpegDecoder
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if dev.index not in _jpeg_decoders:
+            _jpeg_decoders[dev.index] = JpegDecoder(dev)
+        pack["img_u8"] = _jpeg_decoders[dev.index].decode([pack["jpeg"]], size=pack["size"])
     if "img_u8" not in pack:
         return pack
     pyr = preprocess.msf_batch(pack["img_u8"].cuda(non_blocking=True), scales)
@@ -162,10 +180,16 @@ class StepContext:
                                         beta=float(getattr(args, "beta", 10)), exp_times=int(getattr(args, "exp_times", 8)))
         self.writer = Writer(device)
         self._pinned = {}
+        self._jpeg = None
 
     def stack_images(self, packs):
         """The decoded images of a bucket as one device uint8 [N,H,W,3], staged through pinned host memory (two alternating
         buffers per shape; a buffer is rewritten only after the upload that last read it has completed)."""
+        if "jpeg" in packs[0]:       # --device_jpeg: file bytes -> nvJPEG -> uint8 [N,H,W,3] in HBM
+            if self._jpeg is None:
+                from ..jpeg import JpegDecoder
+                self._jpeg = JpegDecoder(self.device)
+            return self._jpeg.decode([p["jpeg"] for p in packs], size=packs[0]["size"])
         N = len(packs)
         shape = (N,) + tuple(packs[0]["img_u8"].shape[1:])
         if shape not in self._pinned and len(self._pinned) >= 8:      # VOC has hundreds of image sizes: bound the pinned pool
@@ -206,7 +230,7 @@ def work_loop(process_id, model, dataset, args, per_image, per_batch=None):
         buckets = {}
         try:
             for it, pack in enumerate(loader):
-                key = (pack["size"], tuple(pack["img_u8"].shape))
+                key = (pack["size"], "jpeg" if "jpeg" in pack else tuple(pack["img_u8"].shape))
                 b = buckets.setdefault(key, [])
                 b.append(pack)
                 if len(b) >= bsz:

@@ -71,8 +71,9 @@ class VOC12ClassificationDatasetMSF(Dataset):
     "size": (H, W), "label": FloatTensor[20]}."""
 
     def __init__(self, img_name_list_path, voc12_root, img_normal=TorchvisionNormalize(), scales=(1.0,),
-                 cls_labels_path="voc12/cls_labels.npy", decode_only=False):
+                 cls_labels_path="voc12/cls_labels.npy", decode_only=False, raw_jpeg=False):
         self.decode_only = decode_only      # hand over the decoded uint8 image; the pyramid is built on the device
+        self.raw_jpeg = raw_jpeg            # hand over the FILE BYTES; nvJPEG decodes them on the device (irn_b200.jpeg)
         self.img_name_list = load_img_name_list(img_name_list_path)
         self.voc12_root = voc12_root
         self.img_normal = img_normal
@@ -85,6 +86,16 @@ class VOC12ClassificationDatasetMSF(Dataset):
 
     def __getitem__(self, idx):
         name_str = decode_int_filename(self.img_name_list[idx])
+        if self.raw_jpeg:
+            path = get_img_path(name_str, self.voc12_root)
+            with Image.open(path) as im:        # header only: the size decides the batch bucket
+                w, h = im.size
+                is_jpeg = im.format == "JPEG" and im.mode == "RGB"
+            if is_jpeg:
+                with open(path, "rb") as f:
+                    data = np.frombuffer(f.read(), dtype=np.uint8).copy()
+                return {"name": name_str, "size": (h, w), "label": torch.from_numpy(self.label_list[idx]), "jpeg": data}
+            # not a 3-component JPEG (grey-scale / PNG stand-ins): decode on the host like the reference
         img = np.asarray(Image.open(get_img_path(name_str, self.voc12_root)).convert("RGB"))
         out = {"name": name_str, "size": (img.shape[0], img.shape[1]), "label": torch.from_numpy(self.label_list[idx])}
         if self.decode_only:
