@@ -14,6 +14,7 @@ and file writes overlap the GPU work of the next batch on a small thread pool.
 import importlib
 import os
 import threading
+import time
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -100,14 +101,22 @@ def attach_pyramid(pack, scales):
 class Writer:
     """File output off the GPU-issuing thread.  A job is `fn(*args)` run on a pool thread after `event` (recorded on the
     compute stream by the submitter) has completed; jobs do their device->host copies on a side stream of their own, so
-    they never queue behind the next batch's kernels.  At most `max_pending` jobs are in flight (bounds host and device
-    memory held by finished batches); exceptions surface in drain()."""
+    they never queue behind the next batch's kernels, and fan the per-image file writes (np.save pickles, PNG encoding: both
+    release the GIL for most of their time) out to a second, wider pool.  At most `max_pending` batch jobs and
+    `max_files` file writes are in flight (bounds host and device memory held by finished batches); exceptions surface in
+    drain()."""
 
-    def __init__(self, device, threads=4, max_pending=8):
+    def __init__(self, device, threads=2, file_threads=None, max_pending=6, max_files=256):
         self.device = device
+        if file_threads is None:
+            n_gpus = max(torch.cuda.device_count(), 1)
+            file_threads = max(4, min(16, (os.cpu_count() or 8) // n_gpus // 2))
         self.pool = ThreadPoolExecutor(max_workers=threads)
+        self.file_pool = ThreadPoolExecutor(max_workers=file_threads)
         self.sem = threading.Semaphore(max_pending)
-        self.futures = []
+        self.file_sem = threading.Semaphore(max_files)
+        self.futures, self.file_futures = [], []
+        self._lock = threading.Lock()
         self._tls = threading.local()
 
     def stream(self):
@@ -147,28 +156,39 @@ class Writer:
         if len(self.futures) > 256:
             self.futures = [f for f in self.futures if not (f.done() and f.exception() is None)]
 
-    def submit_host(self, fn, *args):
-        """A host-only job (no device event to wait for), same back-pressure and error collection."""
-        self.sem.acquire()
+    def submit_file(self, fn, *args):
+        """One file write (host only) on the wide pool; callable from the main thread or from inside a batch job."""
+        self.file_sem.acquire()
 
         def job():
             try:
                 fn(*args)
             finally:
-                self.sem.release()
-        self.futures.append(self.pool.submit(job))
+                self.file_sem.release()
+        f = self.file_pool.submit(job)
+        with self._lock:
+            self.file_futures.append(f)
+            if len(self.file_futures) > 1024:
+                self.file_futures = [x for x in self.file_futures if not (x.done() and x.exception() is None)]
+
+    submit_host = submit_file
 
     def map(self, fn, items):
-        return list(self.pool.map(fn, items))
+        return list(self.file_pool.map(fn, items))
 
     def drain(self):
         for f in self.futures:
             f.result()
         self.futures = []
+        with self._lock:
+            files, self.file_futures = self.file_futures, []
+        for f in files:
+            f.result()
 
     def close(self):
         self.drain()
         self.pool.shutdown()
+        self.file_pool.shutdown()
 
 
 class StepContext:
@@ -228,18 +248,34 @@ def work_loop(process_id, model, dataset, args, per_image, per_batch=None):
             return
         ctx = StepContext(model, args, torch.device("cuda", process_id), scales)
         buckets = {}
+        prof = os.environ.get("IRN_STEP_PROFILE")          # host-side time split of the loop (development aid), printed to stderr
+        t_load = t_body = 0.0
+        t_start = t_prev = time.perf_counter()
         try:
             for it, pack in enumerate(loader):
+                t_now = time.perf_counter()
+                t_load += t_now - t_prev
                 key = (pack["size"], "jpeg" if "jpeg" in pack else tuple(pack["img_u8"].shape))
                 b = buckets.setdefault(key, [])
                 b.append(pack)
                 if len(b) >= bsz:
                     per_batch(ctx, buckets.pop(key))
                 progress(process_id, n_gpus, it, len(shard))
+                t_prev = time.perf_counter()
+                t_body += t_prev - t_now
             for packs in buckets.values():
                 per_batch(ctx, packs)
+            t_loop = time.perf_counter()
+            torch.cuda.synchronize()
+            t_sync = time.perf_counter()
         finally:
             ctx.writer.close()
+        if prof:
+            import sys
+            t_end = time.perf_counter()
+            print("[irn_b200 step profile] rank %d: %d images, %.2f s total = waiting for the loader %.2f + batch bodies (host) %.2f + "
+                  "GPU drain %.2f + file writes drain %.2f" % (process_id, len(shard), t_end - t_start, t_load, t_body, t_sync - t_loop,
+                                                                t_end - t_sync), file=sys.stderr, flush=True)
 
 
 def run_step(args, work, module_name, class_name, weights_path, strict, list_path, scales, opening="[ "):

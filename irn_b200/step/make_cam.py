@@ -24,8 +24,9 @@ def _save(ctx, names, keys, strided, highres, out_dir):
     lo, hi = ctx.writer.to_host([strided, highres])
     o = 0
     for name, k, c in zip(names, keys, counts):
-        np.save(os.path.join(out_dir, name + ".npy"),
-                {"keys": torch.from_numpy(k.astype(np.int64)), "cam": lo[o:o + c].clone(), "high_res": hi[o:o + c].numpy().copy()})
+        # views of the batch's host buffers: pickling copies them, so the buffers live exactly as long as the last write
+        ctx.writer.submit_file(np.save, os.path.join(out_dir, name + ".npy"),
+                               {"keys": torch.from_numpy(k.astype(np.int64)), "cam": lo[o:o + c].clone(), "high_res": hi[o:o + c].numpy()})
         o += c
 
 

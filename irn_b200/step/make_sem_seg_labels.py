@@ -23,7 +23,9 @@ def _save(ctx, names, labels, out_dir):
     (lab,) = ctx.writer.to_host([labels])
     lab = lab.numpy()
     for i, name in enumerate(names):
-        Image.fromarray(lab[i]).save(os.path.join(out_dir, name + ".png"))
+        # compress_level 1: same pixels in the file, a quarter of zlib's time on busy label maps (the default 6 made PNG encoding
+        # the pacer of the whole step: 21 ms per 512x512 map against ~1 ms of GPU time)
+        ctx.writer.submit_file(lambda a, p: Image.fromarray(a).save(p, compress_level=1), lab[i], os.path.join(out_dir, name + ".png"))
 
 
 def sem_seg_batch(ctx, packs):
