@@ -336,7 +336,8 @@ def run_config4(a, rank, world, local, dev, out_stream):
         for name, scales, work, model in (("make_cam", SCALES, make_cam._work, cam), ("make_sem_seg_labels", (1.0,), make_sem_seg_labels._work, irn)):
             t_pass = time.perf_counter()
             ds = vd.VOC12ClassificationDatasetMSF(args.train_list, voc12_root=root, scales=scales, decode_only=True,
-                                                  cls_labels_path="voc12/cls_labels.npy")
+                                                  cls_labels_path="voc12/cls_labels.npy",
+                                                  cam_dir=args.cam_out_dir if name == "make_sem_seg_labels" else None)   # as step.*.run does
             shards = torchutils.split_dataset(ds, world)
             pad = [None] * n_vis
             pad[local] = shards[rank]

@@ -66,17 +66,20 @@ def step_batch(args):
     return max(1, int(getattr(args, "step_batch", DEFAULT_STEP_BATCH) or 1))
 
 
-def make_dataset(args, list_path, scales):
-    """VOC images from --voc12_root, or seeded synthetic ones with --synthetic N."""
+def make_dataset(args, list_path, scales, cam_dir=None):
+    """VOC images from --voc12_root, or seeded synthetic ones with --synthetic N.  `cam_dir`: the label steps let the loader
+    workers read the stored CAM dicts (batched mode only; the one-image loop reads them itself, like the reference)."""
+    if step_batch(args) == 1 or not device_pyramid(args):
+        cam_dir = None
     if getattr(args, "synthetic", 0):
         # one id list for ALL steps (the reference reads --train_list in make_cam but --infer_list in the label steps; with
         # synthetic images the later steps must find the .npy files the first one wrote): --synthetic_list, else 2007_%06d
         names = getattr(args, "synthetic_list", None) or None
         if names is not None and not os.path.exists(names):
             raise FileNotFoundError("--synthetic_list %s" % names)
-        return voc_data.SyntheticMSF(int(args.synthetic), scales=scales, name_list=names, decode_only=device_pyramid(args))
+        return voc_data.SyntheticMSF(int(args.synthetic), scales=scales, name_list=names, decode_only=device_pyramid(args), cam_dir=cam_dir)
     return voc_data.VOC12ClassificationDatasetMSF(list_path, voc12_root=args.voc12_root, scales=scales,
-                                                  decode_only=device_pyramid(args), raw_jpeg=device_jpeg(args))
+                                                  decode_only=device_pyramid(args), raw_jpeg=device_jpeg(args), cam_dir=cam_dir)
 
 
 _jpeg_decoders = {}
@@ -231,6 +234,28 @@ class StepContext:
         return dev
 
 
+def threaded_loader(shard, n_threads, prefetch):
+    """Items of `shard` in order, collated like the batch-size-1 DataLoader, produced by a thread pool instead of forked worker
+    processes: PIL's JPEG decoder and the file reads release the GIL, and a thread hands its arrays over without the
+    shared-memory copy -- and without the ~1 s it takes to fork a dozen workers off a process that holds a CUDA context.  MEASURED
+    SLOWER than the forked workers on the B200 host (the unpickling of the CAM dicts, numpy copies and collation serialise on the
+    GIL: sem-seg pass 9.5 s against 3.1 s), so it is opt-in (--loader_threads True) and kept for hosts where fork is the problem."""
+    from collections import deque
+    n = len(shard)
+    with ThreadPoolExecutor(max_workers=max(1, n_threads)) as pool:
+        pending = deque()
+        nxt = 0
+        while nxt < n and len(pending) < prefetch:
+            pending.append(pool.submit(shard.__getitem__, nxt))
+            nxt += 1
+        while pending:
+            item = pending.popleft().result()
+            if nxt < n:
+                pending.append(pool.submit(shard.__getitem__, nxt))
+                nxt += 1
+            yield collate_one([item])
+
+
 def work_loop(process_id, model, dataset, args, per_image, per_batch=None):
     """One GPU's share: the reference's `_work(process_id, model, dataset, args)` signature and loop order
     (step/make_cam.py:16-59), with the per-image / per-batch body supplied by the step."""
@@ -247,6 +272,8 @@ def work_loop(process_id, model, dataset, args, per_image, per_batch=None):
                 progress(process_id, n_gpus, it, len(shard))
             return
         ctx = StepContext(model, args, torch.device("cuda", process_id), scales)
+        if getattr(args, "loader_threads", False):     # measured slower than forked workers (GIL: 82 vs 148 images/s, bench --config 4): off
+            loader = threaded_loader(shard, max(2, args.num_workers // n_gpus), prefetch=2 * bsz)
         buckets = {}
         prof = os.environ.get("IRN_STEP_PROFILE")          # host-side time split of the loop (development aid), printed to stderr
         t_load = t_body = 0.0
@@ -278,7 +305,7 @@ def work_loop(process_id, model, dataset, args, per_image, per_batch=None):
                                                                 t_end - t_sync), file=sys.stderr, flush=True)
 
 
-def run_step(args, work, module_name, class_name, weights_path, strict, list_path, scales, opening="[ "):
+def run_step(args, work, module_name, class_name, weights_path, strict, list_path, scales, opening="[ ", cam_dir=None):
     """The reference's `run(args)` (e.g. step/make_cam.py:62-77): model class resolved by name, checkpoint loaded,
     stride partition (misc/torchutils.py:66-68), one process per GPU (a single GPU runs in-process)."""
     model = getattr(importlib.import_module(module_name), class_name)()
@@ -287,7 +314,7 @@ def run_step(args, work, module_name, class_name, weights_path, strict, list_pat
     n_gpus = torch.cuda.device_count()
     if n_gpus <= 0:
         raise RuntimeError("irn_b200 steps need at least one CUDA device (there is no CPU fallback)")
-    shards = torchutils.split_dataset(make_dataset(args, list_path, scales), n_gpus)
+    shards = torchutils.split_dataset(make_dataset(args, list_path, scales, cam_dir), n_gpus)
     print(opening, end="")
     if n_gpus == 1:
         work(0, model, shards, args)
@@ -297,6 +324,23 @@ def run_step(args, work, module_name, class_name, weights_path, strict, list_pat
     torch.cuda.empty_cache()
 
 
-def load_cam_dicts(ctx, names, cam_out_dir):
-    """The stored CAMs of make_cam for a batch (np.load(...).item(), step/make_sem_seg_labels.py:34): read on the pool."""
-    return ctx.writer.map(lambda n: np.load(os.path.join(cam_out_dir, n + ".npy"), allow_pickle=True).item(), names)
+def load_cam_dicts(ctx, packs, names, cam_out_dir):
+    """The stored CAMs of make_cam for a batch (np.load(...).item(), step/make_sem_seg_labels.py:34): what the loader workers
+    attached to the items (voc12.dataloader.attach_cam), else read here on the file pool.  Returns (keys list, cam list)."""
+    if "cam" in packs[0]:
+        return [p["cam_keys"][0].numpy() for p in packs], [p["cam"][0] for p in packs]
+    stored = ctx.writer.map(lambda n: np.load(os.path.join(cam_out_dir, n + ".npy"), allow_pickle=True).item(), names)
+    return [np.asarray(s["keys"]) for s in stored], [s["cam"] for s in stored]
+
+
+def to_device_list(ctx, tensors):
+    """A list of small host tensors [K_i,h,w] -> list of device views of ONE uploaded buffer (one H2D copy per batch instead of one
+    per image)."""
+    counts = [int(t.shape[0]) for t in tensors]
+    flat = torch.cat([t.float() for t in tensors], 0) if len(tensors) > 1 else tensors[0].float()
+    dev = flat.to(ctx.device, non_blocking=True)
+    out, o = [], 0
+    for c in counts:
+        out.append(dev[o:o + c])
+        o += c
+    return out

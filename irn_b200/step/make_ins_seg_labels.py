@@ -28,12 +28,11 @@ def ins_seg_batch(ctx, packs):
     every (class, instance) channel of the bucket (irn_b200.pipeline.instance_stage)."""
     args = ctx.args
     names = [p["name"][0] for p in packs]
-    stored = _common.load_cam_dicts(ctx, names, args.cam_out_dir)
+    keys, cams = _common.load_cam_dicts(ctx, packs, names, args.cam_out_dir)
     x = ctx.stack_images(packs)
     x1 = ctx.pipe.pyramids(x, (1.0,))[0]
     edges, dps = ctx.pipe.irn_stage(x1)
-    keys = [np.asarray(s["keys"]) for s in stored]
-    strided = [s["cam"].to(ctx.device, non_blocking=True) for s in stored]
+    strided = _common.to_device_list(ctx, cams)
     dets = ctx.pipe.instance_stage(strided, keys, edges, dps, packs[0]["size"], float(args.ins_seg_bg_thres))
     for name, det in zip(names, dets):
         if det is None:     # the reference's np.stack([]) raises for an image without any detection
@@ -46,4 +45,5 @@ def _work(process_id, model, dataset, args):
 
 
 def run(args):
-    _common.run_step(args, _work, args.irn_network, "EdgeDisplacement", args.irn_weights_name, False, args.infer_list, (1.0,))
+    _common.run_step(args, _work, args.irn_network, "EdgeDisplacement", args.irn_weights_name, False, args.infer_list, (1.0,),
+                     cam_dir=args.cam_out_dir)

@@ -32,12 +32,11 @@ def sem_seg_batch(ctx, packs):
     """step/make_sem_seg_labels.py:28-51 for a bucket of equally-sized images: one IRNet forward, one batched walk."""
     args = ctx.args
     names = [voc_data.decode_int_filename(p["name"][0]) for p in packs]
-    stored = _common.load_cam_dicts(ctx, names, args.cam_out_dir)
+    keys, cams = _common.load_cam_dicts(ctx, packs, names, args.cam_out_dir)
     x = ctx.stack_images(packs)
     x1 = ctx.pipe.pyramids(x, (1.0,))[0]
     edges, _ = ctx.pipe.irn_stage(x1)
-    keys = [np.asarray(s["keys"]) for s in stored]
-    seeds = [s["cam"].to(ctx.device, non_blocking=True) for s in stored]
+    seeds = _common.to_device_list(ctx, cams)
     rw, counts = ctx.pipe.walk_stage(seeds, edges)
     labels = ctx.pipe.label_stage(rw, counts, keys, packs[0]["size"], float(args.sem_seg_bg_thres))
     ctx.writer.submit(_save, ctx, names, labels, args.sem_seg_out_dir)
@@ -48,4 +47,5 @@ def _work(process_id, model, dataset, args):
 
 
 def run(args):
-    _common.run_step(args, _work, args.irn_network, "EdgeDisplacement", args.irn_weights_name, False, args.infer_list, (1.0,), opening="[")
+    _common.run_step(args, _work, args.irn_network, "EdgeDisplacement", args.irn_weights_name, False, args.infer_list, (1.0,), opening="[",
+                     cam_dir=args.cam_out_dir)

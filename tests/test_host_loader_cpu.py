@@ -104,3 +104,32 @@ def test_synthetic_names_are_the_same_for_every_step(tmp_path):
     c = _common.make_dataset(args, str(tmp_path / "train.txt"), (1.0,))
     assert [c[i]["name"] for i in range(2)] == ["2007_000032", "2007_000039"]
     assert _common.step_batch(args) == _common.DEFAULT_STEP_BATCH and _common.step_batch(types.SimpleNamespace(step_batch=1)) == 1
+
+
+def test_loader_attaches_stored_cams(tmp_path):
+    """Label steps in batched mode: the loader worker reads make_cam's .npy (keys + stride-4 CAMs, not the full-resolution maps)
+    and the batch-1 collation keeps them usable (voc12.dataloader.attach_cam, step/_common.load_cam_dicts)."""
+    cam_dir = tmp_path / "cam"
+    os.makedirs(cam_dir)
+    for i in range(2):
+        np.save(cam_dir / ("2007_%06d.npy" % i), {"keys": torch.tensor([3, 11]), "cam": torch.full((2, 8, 12), float(i)),
+                                                    "high_res": np.zeros((2, 32, 48), np.float32)})
+    ds = dl.SyntheticMSF(2, size=(32, 48), scales=(1.0,), decode_only=True, cam_dir=str(cam_dir))
+    pack = _common.collate_one([ds[1]])
+    assert pack["cam"].shape == (1, 2, 8, 12) and float(pack["cam"].max()) == 1.0 and pack["cam_keys"].tolist() == [[3, 11]]
+    args = types.SimpleNamespace(synthetic=2, voc12_root="", step_batch=1)
+    assert _common.make_dataset(args, "x", (1.0,), cam_dir=str(cam_dir)).cam_dir is None      # one-image loop: the step reads the file itself
+    args.step_batch = 8
+    assert _common.make_dataset(args, "x", (1.0,), cam_dir=str(cam_dir)).cam_dir == str(cam_dir)
+
+
+def test_threaded_loader_matches_dataloader_order():
+    """Batched mode's thread-pool loader: same items, same order, same batch-1 collation as the DataLoader it replaces."""
+    ds = dl.SyntheticMSF(7, size=(24, 32), scales=(1.0,), decode_only=True)
+    shard = torchutils.split_dataset(ds, 2)[1]
+    got = list(_common.threaded_loader(shard, 3, prefetch=4))
+    assert [p["name"] for p in got] == [["2007_%06d" % i] for i in (1, 3, 5)]
+    from torch.utils.data import DataLoader
+    ref = list(DataLoader(shard, shuffle=False, num_workers=0, collate_fn=_common.collate_one))
+    for a, b in zip(got, ref):
+        assert a["size"] == b["size"] and torch.equal(a["img_u8"], b["img_u8"]) and torch.equal(a["label"], b["label"])

@@ -29,25 +29,25 @@ for cin, cout, k, s, H, W, res in [(64, 64, 3, 1, 20, 24, False), (64, 256, 1, 1
                                    (512, 1024, 1, 2, 16, 16, False)]:
     w_ = (torch.randn(cout, cin, k, k) * 0.05).numpy()
     conv = Conv2d(w_, None, s, k // 2)
-    x = torch.randn(2, H, W, cin, device=dev)
+    x = torch.randn(2, H, W, cin).to(dev)            # host-generated + H2D copy: initcheck does not see PyTorch's own generator kernels' writes
     Ho = (H + 2 * (k // 2) - k) // s + 1
     Wo = (W + 2 * (k // 2) - k) // s + 1
-    r = torch.randn(2, Ho, Wo, cout, device=dev) if res else None
+    r = torch.randn(2, Ho, Wo, cout).to(dev) if res else None
     for mode in (1, 2):
         conv(x, r, relu=True, mode=mode)
     torch.cuda.synchronize()
     print("conv", cin, cout, k, s, "ok", flush=True)
 
 # labels, merge, instance kernels, pyramids
-rw = torch.rand(3, 20, 24, device=dev)
+rw = torch.rand(3, 20, 24).to(dev)
 indexing.rw_labels(rw, [1, 4, 7], (78, 95), want_index=True, want_scores=True)
-cams = [torch.rand(20, s_, s_ + 1, device=dev) for s_ in (5, 3, 8, 10)]
+cams = [torch.rand(20, s_, s_ + 1).to(dev) for s_ in (5, 3, 8, 10)]
 lab = np.zeros(20, np.float32); lab[[2, 9]] = 1
 cam_ops.merge_cams(cams, (78, 95), lab)
 dp = t(synth.displacement(20, 24, 3, 1))
 cen = instance.find_centroids_with_refinement(dp, iterations=20)
 inst, n = instance.cluster_centroids(cen, dp)
-seeds = instance.separate_score_by_mask(torch.rand(2, 20, 24, device=dev), inst, n)
+seeds = instance.separate_score_by_mask(torch.rand(2, 20, 24).to(dev), inst, n)
 _, idx, sc = indexing.rw_labels(seeds.reshape(-1, 20, 24), None, (78, 95), want_index=True, want_scores=True)
 instance.detect_instance(sc, idx, np.repeat([1, 2], n), 10)
 preprocess.msf_batch(t(synth.image(1, 37, 50)[None]), (1.0, 0.5, 1.5))
