@@ -307,6 +307,7 @@ conv_f16_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
             tma_prefetch_desc(&maps.a);
             tma_prefetch_desc(&maps.b_hi);
             tma_prefetch_desc(&maps.b_lo);
+            if (args.kb_split < KB) tma_prefetch_desc(&maps.a2);
         }
         uint32_t g = 0;
         for (int id = blockIdx.x; id < total; id += gridDim.x) {
@@ -317,12 +318,24 @@ conv_f16_kernel(const __grid_constant__ TcMaps maps, const TcArgs args) {
                 mbar_wait(&empty[s], (it & 1) ^ 1);
                 if (elect_one()) {
                     unsigned char* st = smem + s * Cfg::kStageBytes;
-                    const int tap = kb / cblocks, cb = kb % cblocks;
+                    // K-concatenated 1x1 conv: k-blocks from kb_split on come from the second input (its own pixel stride, no padding)
+                    const bool second = kb >= args.kb_split;
+                    const CUtensorMap* am = second ? &maps.a2 : &maps.a;
+                    const int tap = second ? 0 : kb / cblocks, cb = second ? kb - args.kb_split : kb % cblocks;
                     const int r = tap / args.ksize, ss = tap % args.ksize;
-                    const int x = ox0 * args.stride - args.pad + ss, y = oy0 * args.stride - args.pad + r;
+                    const int x = second ? ox0 * args.stride2 : ox0 * args.stride - args.pad + ss;
+                    const int y = second ? oy0 * args.stride2 : oy0 * args.stride - args.pad + r;
                     mbar_arrive_expect_tx(&full[s], (uint32_t)Cfg::kStageBytes);
-                    tma_load_4d(st, &maps.a, &full[s], cb * kBfBK, x, y, b);
-                    tma_load_4d(st + 16384, &maps.a, &full[s], cb * kBfBK + 32, x, y, b);
+                    if (args.mode & 1) {
+                        // 7x7 / stride-2 stem over the zero-haloed NHWC4 input: the 32 floats of a row are the 8 taps x 4 channels of
+                        // ONE filter row for one output pixel (overlapping windows, nets.cu launch_f16_stem); a k-block = filter rows
+                        // 2 kb and 2 kb + 1 (row 7 carries zero weights)
+                        tma_load_4d(st, &maps.a, &full[s], 0, ox0, oy0 * 2 + 2 * kb, b);
+                        tma_load_4d(st + 16384, &maps.a, &full[s], 0, ox0, oy0 * 2 + 2 * kb + 1, b);
+                    } else {
+                        tma_load_4d(st, am, &full[s], cb * kBfBK, x, y, b);
+                        tma_load_4d(st + 16384, am, &full[s], cb * kBfBK + 32, x, y, b);
+                    }
                     tma_load_2d(st + 32768, &maps.b_hi, &full[s], kb * kBfBK, n0);
                     tma_load_2d(st + 32768 + Cfg::kBBytes, &maps.b_lo, &full[s], kb * kBfBK, n0);
                 }

@@ -33,6 +33,7 @@ struct TcMaps {
     CUtensorMap a;      // input  {Cin, W, H, B}
     CUtensorMap b_hi;   // weights {K, Cout}
     CUtensorMap b_lo;
+    CUtensorMap a2;     // conv_f16_kernel only: second input of a K-concatenated 1x1 conv (TcArgs::kb_split); unused otherwise
 };
 
 struct TcArgs {
@@ -41,6 +42,8 @@ struct TcArgs {
     float* out;
     int B, Ho, Wo, Cout, Cin, ksize, stride, pad, relu;
     int tiles_x, tiles_y;
+    int kb_split = 1 << 30;          // conv_f16_kernel only: k-blocks [kb_split, KB) read input `a2` (pixel stride `stride2`): the projection
+    int stride2 = 1;                 // shortcut of a bottleneck fused into conv3's reduction (nets.cu, Block::c3ds)
     const float* oscale = nullptr;   // conv_f16.cuh only: per-output-channel factor undoing the weights' power-of-two pre-scale
     int mode;   // 0: NHWC input, one k-block per (tap, 32-channel slice); 1: stem, NHWC4 zero-haloed input, one k-block per filter row
 };

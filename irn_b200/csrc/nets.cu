@@ -38,6 +38,7 @@ struct Conv {
     float* oscale = nullptr;
     bool bf_ok = false;
     CUtensorMap map_bf_hi[2], map_bf_lo[2];   // N tile 64, 128 (the latter only when cout allows)
+    std::vector<float> host_wt, host_bias;   // folded fp32 weights [K][cout] / bias, kept on the host until the plan is complete
     bool stem_tc = false;    // 7x7/s2 stem repacked as 7 k-blocks of (8 taps x 4 channels) over a zero-haloed NHWC4 input
 };
 
@@ -51,6 +52,10 @@ struct Head {            // conv1x1 (no bias) -> GroupNorm(groups) -> [upsample]
 struct Block {
     Conv c1, c2, c3, ds;
     bool has_ds = false;
+    // f16x3 mode: conv3 and the projection shortcut as ONE K-concatenated 1x1 conv, out = relu([W3 | Wds] . [t2 ; x_strided] + b3 + bds):
+    // the shortcut tensor (as wide as the block's output) is neither written nor read back
+    Conv c3ds;
+    bool has_c3ds = false;
 };
 
 }  // namespace irn
@@ -59,6 +64,7 @@ struct irn_net {
     int kind = 0;   // 0 = CAM, 1 = IRN (EdgeDisplacement)
     int conv_mode = 2;   // 0 = SIMT exact-fp32 convolutions only, 1 = tcgen05 3xTF32 where eligible, 2 = tcgen05 f16x3 (default; 3xTF32 / SIMT for the layers it cannot take)
     irn::Conv stem;
+    irn::Conv stem_f16;            // the stem repacked for the f16x3 kernel (K = 256 over the NHWC4 halo layout)
     std::vector<irn::Block> blocks[4];
     // CAM
     float* classifier = nullptr;   // [20][2048] (SIMT head kernel)
@@ -133,6 +139,8 @@ static int read_conv(irn_net* net, Reader& rd, Conv& c, int cin, int cout, int k
     int rc = upload(net, wt, &c.wt);
     if (rc) return rc;
     if (bn && (rc = upload(net, bias, &c.bias))) return rc;
+    c.host_wt = wt;
+    c.host_bias = bias;
     if ((rc = make_bf16_weights(net, c, wt))) return rc;
     // tensor-core eligibility: 32-channel k slices, 64/128-wide N tiles, 1x1 or 3x3, stride 1 or 2
     c.bn = (cout % 128 == 0) ? 128 : (cout % 64 == 0 ? 64 : 0);
@@ -249,6 +257,17 @@ static int read_trunk(irn_net* net, Reader& rd) {
         if ((rc = make_tensor_map(&c.map_bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
         if ((rc = make_tensor_map(&c.map_blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c.w_lo, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
         c.stem_tc = true;
+        // f16x3 stem: the same rows, K = 8 filter rows x 32 (row 7 zero) = 256 = four 64-wide k-blocks
+        Conv& f = net->stem_f16;
+        f.cin = 256; f.cout = 64; f.k = 1; f.stride = 1; f.pad = 0;
+        std::vector<float> wt((size_t)256 * 64, 0.f);
+        for (int o = 0; o < 64; ++o)
+            for (int r = 0; r < 7; ++r)
+                for (int t = 0; t < 7; ++t)
+                    for (int ci = 0; ci < 3; ++ci)
+                        wt[(size_t)(r * 32 + t * 4 + ci) * 64 + o] = host[((size_t)(r * 7 + t) * 3 + ci) * 64 + o];
+        f.bias = c.bias;
+        if ((rc = make_bf16_weights(net, f, wt))) return rc;
     }
     int cin = 64;
     for (int l = 0; l < 4; ++l) {
@@ -261,9 +280,29 @@ static int read_trunk(irn_net* net, Reader& rd) {
             if ((rc = read_conv(net, rd, blk.c3, planes, planes * 4, 1, 1, 0, true))) return rc;
             blk.has_ds = b == 0;
             if (blk.has_ds && (rc = read_conv(net, rd, blk.ds, cin, planes * 4, 1, stride, 0, true))) return rc;
+            if (blk.has_ds && planes % kBfBK == 0 && cin % kBfBK == 0) {
+                Conv& f = blk.c3ds;
+                const int cout = planes * 4, K3 = planes, Kd = cin;
+                f.cin = K3 + Kd; f.cout = cout; f.k = 1; f.stride = 1; f.pad = 0;
+                std::vector<float> wt((size_t)(K3 + Kd) * cout), bias(cout);
+                std::copy(blk.c3.host_wt.begin(), blk.c3.host_wt.end(), wt.begin());
+                std::copy(blk.ds.host_wt.begin(), blk.ds.host_wt.end(), wt.begin() + (size_t)K3 * cout);
+                for (int o = 0; o < cout; ++o) bias[o] = blk.c3.host_bias[o] + blk.ds.host_bias[o];
+                if ((rc = upload(net, bias, &f.bias))) return rc;
+                if ((rc = make_bf16_weights(net, f, wt))) return rc;
+                blk.has_c3ds = f.bf_ok;
+            }
             cin = planes * 4;
         }
     }
+    // the host copies were only needed to build the fused convs
+    net->stem.host_wt.clear(); net->stem.host_wt.shrink_to_fit();
+    for (int l = 0; l < 4; ++l)
+        for (Block& blk : net->blocks[l])
+            for (Conv* c : {&blk.c1, &blk.c2, &blk.c3, &blk.ds}) {
+                std::vector<float>().swap(c->host_wt);
+                std::vector<float>().swap(c->host_bias);
+            }
     return kOk;
 }
 
@@ -465,9 +504,15 @@ static int f16_mode_flags() {
     return spin ? 0 : 4;
 }
 
+// Second input of a K-concatenated 1x1 conv (Block::c3ds): NHWC [B, H2, W2, cin2] sampled with pixel stride `stride`
+struct F16Second {
+    const float* in = nullptr;
+    int H = 0, W = 0, cin = 0, stride = 1;
+};
+
 template <int BN, int NACC, int NSLOT, bool HALO>
 static int launch_f16(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
-                      cudaStream_t st) {
+                      cudaStream_t st, const F16Second* second = nullptr) {
     using Cfg = F16Cfg<BN, NACC, NSLOT>;
     constexpr size_t smem = HALO ? Cfg::kSmemHalo : Cfg::kSmem;
     static DeviceOnce once;
@@ -486,12 +531,22 @@ static int launch_f16(const Conv& c, const float* in, int B, int H, int W, int H
     TcMaps maps;
     maps.b_hi = c.map_bf_hi[mi];
     maps.b_lo = c.map_bf_lo[mi];
-    const uint64_t dims[4] = {(uint64_t)c.cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    const uint64_t strides[3] = {(uint64_t)c.cin * 4, (uint64_t)W * c.cin * 4, (uint64_t)H * W * c.cin * 4};
+    const int cin1 = second ? c.cin - second->cin : c.cin;        // channels of the first input
+    const uint64_t dims[4] = {(uint64_t)cin1, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)cin1 * 4, (uint64_t)W * cin1 * 4, (uint64_t)H * W * cin1 * 4};
     const uint32_t box[4] = {32u, (uint32_t)(HALO ? kHaloW : kTcTW * c.stride), (uint32_t)(HALO ? kHaloH : kTcTH * c.stride), 1};
     const uint32_t estr[4] = {1, (uint32_t)(HALO ? 1 : c.stride), (uint32_t)(HALO ? 1 : c.stride), 1};
     int rc = make_tensor_map(&maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, estr);
     if (rc) return rc;
+    maps.a2 = maps.a;
+    if (second) {
+        if (HALO || c.k != 1) return fail(kUnsupported, "launch_f16: a second input needs the plain 1x1 kernel");
+        const uint64_t d2[4] = {(uint64_t)second->cin, (uint64_t)second->W, (uint64_t)second->H, (uint64_t)B};
+        const uint64_t s2[3] = {(uint64_t)second->cin * 4, (uint64_t)second->W * second->cin * 4, (uint64_t)second->H * second->W * second->cin * 4};
+        const uint32_t b2[4] = {32u, (uint32_t)(kTcTW * second->stride), (uint32_t)(kTcTH * second->stride), 1};
+        const uint32_t e2[4] = {1, (uint32_t)second->stride, (uint32_t)second->stride, 1};
+        if ((rc = make_tensor_map(&maps.a2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, second->in, d2, s2, b2, CU_TENSOR_MAP_SWIZZLE_128B, e2))) return rc;
+    }
     TcArgs a;
     a.bias = c.bias; a.residual = residual; a.out = out;
     a.oscale = c.oscale;
@@ -500,6 +555,10 @@ static int launch_f16(const Conv& c, const float* in, int B, int H, int W, int H
     a.tiles_x = (Wo + kTcTW - 1) / kTcTW;
     a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
     a.mode = f16_mode_flags();
+    if (second) {
+        a.kb_split = cin1 / kBfBK;
+        a.stride2 = second->stride;
+    }
     const long long total = (long long)a.tiles_x * a.tiles_y * B * (c.cout / BN);
     const int n_sm = once.n_sm[ds];
     const unsigned grid = (unsigned)(total < n_sm ? total : n_sm);
@@ -513,21 +572,61 @@ static int launch_f16(const Conv& c, const float* in, int B, int H, int W, int H
     return kOk;
 }
 
+// 7x7 / stride-2 stem on the f16x3 kernel: x4 = zero-haloed NHWC4 input [B, Hin+6, Win+8, 4] (as for launch_tc_stem)
+static int launch_f16_stem(const Conv& c, const float* x4, int B, int Hin, int Win, float* out, cudaStream_t st) {
+    using Cfg = F16Cfg<64, 1, 4>;
+    static DeviceOnce once;
+    const int ds = once.slot();
+    if (once.need(ds)) {
+        IRN_CUDA(cudaFuncSetAttribute((conv_f16_kernel<64, 1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+        int dev = 0;
+        IRN_CUDA(cudaGetDevice(&dev));
+        IRN_CUDA(cudaDeviceGetAttribute(&once.n_sm[ds], cudaDevAttrMultiProcessorCount, dev));
+        once.done[ds] = true;
+    }
+    const int Hp = Hin + 6, Wp = Win + 8;
+    const int Ho = conv_out(Hin, 7, 2, 3), Wo = conv_out(Win, 7, 2, 3);
+    TcMaps maps;
+    maps.b_hi = c.map_bf_hi[0];
+    maps.b_lo = c.map_bf_lo[0];
+    // dim0: the 32 contiguous floats (8 px x 4 ch) of one filter-row window; dim1: output column (windows overlap: stride 2 px = 32 B);
+    // dim2: padded input row; dim3: image
+    const uint64_t dims[4] = {32, (uint64_t)Wo, (uint64_t)Hp, (uint64_t)B};
+    const uint64_t strides[3] = {32, (uint64_t)Wp * 16, (uint64_t)Hp * Wp * 16};
+    const uint32_t box[4] = {32, (uint32_t)kTcTW, (uint32_t)(kTcTH * 2), 1};
+    const uint32_t estr[4] = {1, 1, 2, 1};
+    int rc = make_tensor_map(&maps.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, estr);
+    if (rc) return rc;
+    maps.a2 = maps.a;
+    TcArgs a;
+    a.bias = c.bias; a.residual = nullptr; a.out = out;
+    a.oscale = c.oscale;
+    a.B = B; a.Ho = Ho; a.Wo = Wo; a.Cout = 64; a.Cin = 256; a.ksize = 1; a.stride = 2; a.pad = 0; a.relu = 1;
+    a.tiles_x = (Wo + kTcTW - 1) / kTcTW;
+    a.tiles_y = (Ho + kTcTH - 1) / kTcTH;
+    a.mode = f16_mode_flags() | 1;
+    const long long total = (long long)a.tiles_x * a.tiles_y * B;
+    const int n_sm = once.n_sm[ds];
+    conv_f16_kernel<64, 1, 4><<<(unsigned)(total < n_sm ? total : n_sm), kBfThreads, Cfg::kSmem, st>>>(maps, a);
+    IRN_LAUNCH_CHECK("conv_f16_kernel(stem)");
+    return kOk;
+}
+
 // f16x3 dispatch.  Reductions with K >= 512 keep the hi*hi and the cross terms in separate TMEM accumulators (the tensor core's
 // accumulate truncates: conv_f16.cuh, f16_issue3), shorter ones use one accumulator per tile and two accumulator sets so that the
 // epilogue of a tile overlaps the next tile's mainloop (they are memory-bound).  3x3 / stride 1 convs take the halo-tile kernel.
 template <bool HALO>
 static int dispatch_f16(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
-                        cudaStream_t st) {
+                        cudaStream_t st, const F16Second* second = nullptr) {
     const int K = c.k * c.k * c.cin;
     static const int acc_min_k = getenv("IRN_F16_ACC_MINK") ? atoi(getenv("IRN_F16_ACC_MINK")) : 512;
     const bool sep = K >= acc_min_k;
     if (c.cout % 128 == 0) {
-        if (sep) return launch_f16<128, 2, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
-        return launch_f16<128, 1, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+        if (sep) return launch_f16<128, 2, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st, second);
+        return launch_f16<128, 1, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st, second);
     }
-    if (sep) return launch_f16<64, 2, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
-    return launch_f16<64, 1, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st);
+    if (sep) return launch_f16<64, 2, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st, second);
+    return launch_f16<64, 1, 4, HALO>(c, in, B, H, W, Ho, Wo, residual, out, relu, st, second);
 }
 
 static int run_conv_bf16(const Conv& c, const float* in, int B, int H, int W, int Ho, int Wo, const float* residual, float* out, bool relu,
@@ -632,7 +731,10 @@ static int run_trunk(const irn_net* net, const float* x_nchw, int B, int H, int 
         const size_t total = (size_t)B * (Hin + 6) * (Win + 8);
         nchw_to_nhwc4_halo_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nchw, (float4*)x_in, B, H, W, Hin + 6, Win + 8);
         IRN_LAUNCH_CHECK("nchw_to_nhwc4_halo_kernel");
-        if ((rc = launch_tc_stem(net->stem, x_in, B, Hin, Win, stem_out, st))) return rc;
+        static const int stem_f16 = getenv("IRN_F16_STEM") ? atoi(getenv("IRN_F16_STEM")) : 1;
+        if (net->conv_mode == 2 && net->stem_f16.bf_ok && stem_f16) {
+            if ((rc = launch_f16_stem(net->stem_f16, x_in, B, Hin, Win, stem_out, st))) return rc;
+        } else if ((rc = launch_tc_stem(net->stem, x_in, B, Hin, Win, stem_out, st))) return rc;
     } else {
         const size_t total = (size_t)B * Hin * Win * 3;
         nchw_to_nhwc_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nchw, x_in, B, 3, H, W, Hin, Win);
@@ -654,8 +756,10 @@ static int run_trunk(const irn_net* net, const float* x_nchw, int B, int H, int 
             int ho, wo;
             if ((rc = run_conv(net, blk.c1, x, B, h, w, nullptr, t1, true, st, nullptr, nullptr))) return rc;
             if ((rc = run_conv(net, blk.c2, t1, B, h, w, nullptr, t2, true, st, &ho, &wo))) return rc;
+            static const int fuse_ds = getenv("IRN_F16_FUSE_DS") ? atoi(getenv("IRN_F16_FUSE_DS")) : 1;
+            const bool fused = net->conv_mode == 2 && blk.has_c3ds && fuse_ds;
             const float* res = x;
-            if (blk.has_ds) {
+            if (blk.has_ds && !fused) {
                 if ((rc = run_conv(net, blk.ds, x, B, h, w, nullptr, dsb, false, st, nullptr, nullptr))) return rc;
                 res = dsb;
             }
@@ -667,7 +771,11 @@ static int run_trunk(const irn_net* net, const float* x_nchw, int B, int H, int 
                 out = ping[flip];
                 flip ^= 1;
             }
-            if ((rc = run_conv(net, blk.c3, t2, B, ho, wo, res, out, true, st, nullptr, nullptr))) return rc;   // out += residual; relu (net/resnet50.py:51-52)
+            if (fused) {   // conv3 + projection shortcut in one reduction: [t2 ; x sampled at the block's stride]
+                F16Second sec;
+                sec.in = x; sec.H = h; sec.W = w; sec.cin = blk.ds.cin; sec.stride = blk.ds.stride;
+                if ((rc = dispatch_f16<false>(blk.c3ds, t2, B, ho, wo, ho, wo, nullptr, out, true, st, &sec))) return rc;
+            } else if ((rc = run_conv(net, blk.c3, t2, B, ho, wo, res, out, true, st, nullptr, nullptr))) return rc;   // out += residual; relu (net/resnet50.py:51-52)
             x = out;
             h = ho;
             w = wo;
