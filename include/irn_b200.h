@@ -60,6 +60,20 @@ int irn_edge_to_affinity(const float* edge, float* aff, int n_img, int h, int w,
                          irn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * N4  training-side affinity.  Replaces net/resnet50_irn.py:162-175
+ * (AffinityDisplacementLoss.to_affinity: index_select over PathIndex.path_indices +
+ * max_pool2d over the path) and its autograd backward.  edge fp32 [n_img,h,w];
+ * aff fp32 [n_img, n_dst, (h-rf)*(w-2rf)], rf = radius-1 (the source window of PathIndex);
+ * arg int32, same shape: flat index h*w of the path point that held the maximum (first in
+ * path order, as max_pool2d), NULL when no backward pass will follow.  backward: zeroes
+ * grad_edge [n_img,h,w], then grad_edge[arg] -= grad_aff (atomic adds, like index_add_).
+ */
+int irn_to_affinity_forward(const float* edge, float* aff, int32_t* arg, int n_img, int h, int w,
+                            int radius, irn_stream_t stream);
+int irn_to_affinity_backward(const float* grad_aff, const int32_t* arg, float* grad_edge, int n_img,
+                             int h, int w, int radius, irn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * R3-R6  random walk.  Replaces misc/indexing.py:141-167 (propagate_to_edge) including
  * affinity_sparse2dense (:112-129) and to_transition_matrix (:132-139): instead of the
  * dense (hw)^2 matrix squared exp_times times it applies the 2*n_dst+1 tap stencil

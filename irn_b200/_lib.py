@@ -21,6 +21,8 @@ SIGNATURES = {
     "irn_path_index_shape": (c_int, [c_int, _p_int, _p_int, _p_int, _p_int]),
     "irn_path_index_fill": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "irn_edge_to_affinity": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "irn_to_affinity_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "irn_to_affinity_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "irn_rw_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "irn_random_walk": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_double, c_int,
                                 c_void_p, c_size_t, c_void_p]),

@@ -147,6 +147,58 @@ rw_affinity_kernel(const float* __restrict__ edge, float* __restrict__ out, int 
     }
 }
 
+// ---------------------------------------------------------------- training-side affinity
+// AffinityDisplacementLoss.to_affinity (net/resnet50_irn.py:162-175): the same gather + max over path points as
+// edge_to_affinity, on the cropped source window of PathIndex (rows [0, h-rf), columns [rf, w-rf): every path stays inside the
+// image), output [n_img, n_dst, (h-rf)*(w-2rf)].  `arg` records which path point held the maximum -- the FIRST one in path
+// order, like max_pool2d -- so that the backward pass can route the gradient the way autograd does through
+// max_pool2d + index_select.
+__global__ void __launch_bounds__(kAffTX* kAffTY)
+aff_train_fwd_kernel(const float* __restrict__ edge, float* __restrict__ aff, int* __restrict__ arg, int h, int w) {
+    extern __shared__ float s_edge[];   // [(TY + R) x (TX + 2R)], R = radius - 1
+    const int R = c_tab.radius - 1;
+    const int ch = h - R, cw = w - 2 * R;
+    const int SW = kAffTX + 2 * R;
+    const int tiles_x = (cw + kAffTX - 1) / kAffTX;
+    const int x0 = (blockIdx.x % tiles_x) * kAffTX, y0 = (blockIdx.x / tiles_x) * kAffTY;   // window coordinates
+    const int img = blockIdx.y;
+    const float* e = edge + (size_t)img * h * w;
+    const int n = (kAffTY + R) * SW;
+    for (int i = threadIdx.y * kAffTX + threadIdx.x; i < n; i += kAffTX * kAffTY) {
+        const int yy = y0 + i / SW, xx = x0 + i % SW;          // image column of window column c is c + R; the tile starts R to its left
+        s_edge[i] = (yy < h && xx < w) ? e[(size_t)yy * w + xx] : 0.f;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= cw || y >= ch) return;
+    const int n_dst = c_tab.n_dst;
+    const size_t n_src = (size_t)ch * cw;
+    const size_t o = (size_t)img * n_dst * n_src + (size_t)y * cw + x;
+    for (int k = 0; k < n_dst; ++k) {
+        float m = -INFINITY;
+        int at = 0;
+        for (int j = c_tab.pstart[k]; j < c_tab.pstart[k + 1]; ++j) {
+            const int py = c_tab.py[j], px = c_tab.px[j];
+            const float v = s_edge[(threadIdx.y + py) * SW + threadIdx.x + R + px];
+            if (v > m || v != v) {      // strictly greater: the first maximum wins; NaN propagates (max_pool2d)
+                m = v;
+                at = (y + py) * w + x + R + px;
+            }
+        }
+        aff[o + (size_t)k * n_src] = 1.0f - m;   // net/resnet50_irn.py:171
+        if (arg) arg[o + (size_t)k * n_src] = at;
+    }
+}
+
+// d aff / d edge: aff = 1 - edge[arg]  ->  grad_edge[arg] -= grad_aff (index_select's backward is the same scatter-add)
+__global__ void aff_train_bwd_kernel(const float* __restrict__ grad_aff, const int* __restrict__ arg, float* __restrict__ grad_edge,
+                                     size_t per_img, size_t hw, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t img = i / per_img;
+    atomicAdd(grad_edge + img * hw + arg[i], -grad_aff[i]);
+}
+
 // inv_s[p] = 1 / (1 + sum_k W_k(p) + sum_k W_k(p - d_k))      (misc/indexing.py:124,135)
 __global__ void rw_rowsum_kernel(const float* __restrict__ W, double* __restrict__ inv_s, int h, int w, int pitch) {
     const int img = blockIdx.y;
@@ -1014,6 +1066,44 @@ extern "C" int irn_edge_to_affinity(const float* edge, float* aff, int n_img, in
     const size_t smem = (size_t)(kAffTY + R) * (kAffTX + 2 * R) * sizeof(float);
     rw_affinity_kernel<1><<<grid, block, smem, stream>>>(edge, aff, h, w, w, 1.0, 1);
     IRN_LAUNCH_CHECK("rw_affinity_kernel<1>");
+    return kOk;
+}
+
+extern "C" int irn_to_affinity_forward(const float* edge, float* aff, int32_t* arg, int n_img, int h, int w, int radius,
+                                       irn_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    launch_counter() = 0;
+    if (!edge || !aff || n_img <= 0 || h <= 0 || w <= 0) return fail(kBadArg, "irn_to_affinity_forward: bad argument");
+    if (radius < 2 || radius > 10) return fail(kUnsupported, "irn_to_affinity_forward: radius %d outside [2,10]", radius);
+    const int R = radius - 1;
+    const int ch = h - R, cw = w - 2 * R;
+    if (ch <= 0 || cw <= 0) return fail(kBadArg, "irn_to_affinity_forward: grid %dx%d too small for radius %d", h, w, radius);
+    if ((size_t)h * w >= (1u << 31)) return fail(kUnsupported, "irn_to_affinity_forward: grid too large");
+    int rc = upload_tables(radius, stream, nullptr);
+    if (rc) return rc;
+    dim3 grid(((cw + kAffTX - 1) / kAffTX) * ((ch + kAffTY - 1) / kAffTY), n_img), block(kAffTX, kAffTY);
+    const size_t smem = (size_t)(kAffTY + R) * (kAffTX + 2 * R) * sizeof(float);
+    aff_train_fwd_kernel<<<grid, block, smem, stream>>>(edge, aff, arg, h, w);
+    IRN_LAUNCH_CHECK("aff_train_fwd_kernel");
+    return kOk;
+}
+
+extern "C" int irn_to_affinity_backward(const float* grad_aff, const int32_t* arg, float* grad_edge, int n_img, int h, int w,
+                                        int radius, irn_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    launch_counter() = 0;
+    if (!grad_aff || !arg || !grad_edge || n_img <= 0 || h <= 0 || w <= 0) return fail(kBadArg, "irn_to_affinity_backward: bad argument");
+    if (radius < 2 || radius > 10) return fail(kUnsupported, "irn_to_affinity_backward: radius %d outside [2,10]", radius);
+    const int R = radius - 1;
+    const int ch = h - R, cw = w - 2 * R;
+    if (ch <= 0 || cw <= 0) return fail(kBadArg, "irn_to_affinity_backward: grid %dx%d too small for radius %d", h, w, radius);
+    int n_dst = 0;
+    int rc = upload_tables(radius, stream, &n_dst);
+    if (rc) return rc;
+    const size_t per_img = (size_t)n_dst * ch * cw, total = per_img * n_img;
+    IRN_CUDA(cudaMemsetAsync(grad_edge, 0, (size_t)n_img * h * w * sizeof(float), stream));
+    aff_train_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(grad_aff, arg, grad_edge, per_img, (size_t)h * w, total);
+    IRN_LAUNCH_CHECK("aff_train_bwd_kernel");
     return kOk;
 }
 

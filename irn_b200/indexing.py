@@ -87,6 +87,62 @@ def edge_to_affinity(edge, radius=5):
     return out
 
 
+class _ToAffinity(torch.autograd.Function):
+    """Forward/backward pair behind `to_affinity`: one gather-max kernel that remembers where each maximum was, one scatter."""
+
+    @staticmethod
+    def forward(ctx, edge, radius):
+        B, h, w = edge.shape
+        rf = int(radius) - 1
+        n_dst = ctypes.c_int()
+        L = _lib.lib()
+        _lib.check(L.irn_path_index_shape(int(radius), ctypes.byref(n_dst), None, None, None))
+        n_src = (h - rf) * (w - 2 * rf)
+        if h - rf <= 0 or w - 2 * rf <= 0:
+            raise _lib.IrnError("to_affinity: grid %dx%d too small for radius %d" % (h, w, radius))
+        e = edge.detach().contiguous().float()
+        aff = torch.empty((B, n_dst.value, n_src), dtype=torch.float32, device=e.device)
+        need_grad = edge.requires_grad
+        arg = torch.empty((B, n_dst.value, n_src), dtype=torch.int32, device=e.device) if need_grad else None
+        with torch.cuda.device(e.device):
+            _lib.check(L.irn_to_affinity_forward(_lib.ptr(e), _lib.ptr(aff), _lib.ptr(arg) if need_grad else None, B, h, w, int(radius),
+                                                 _lib.stream_ptr()), "irn_to_affinity_forward")
+        ctx.shape, ctx.radius = (B, h, w), int(radius)
+        if need_grad:
+            ctx.save_for_backward(arg)
+        return aff
+
+    @staticmethod
+    def backward(ctx, grad_aff):
+        (arg,) = ctx.saved_tensors
+        B, h, w = ctx.shape
+        g = grad_aff.contiguous().float()
+        grad_edge = torch.empty((B, h, w), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().irn_to_affinity_backward(_lib.ptr(g), _lib.ptr(arg), _lib.ptr(grad_edge), B, h, w, ctx.radius,
+                                                           _lib.stream_ptr()), "irn_to_affinity_backward")
+        return grad_edge, None
+
+
+def to_affinity(edge, path_index=None, radius=None):
+    """Drop-in body for `AffinityDisplacementLoss.to_affinity` (net/resnet50_irn.py:162-175), differentiable: edge cuda fp32
+    [B,1,H,W] (what train_irn passes: sigmoid(edge_out)) or [B,H,W]; returns aff [B, n_dst, (H-rf)*(W-2rf)] in
+    PathIndex.search_dst order.  The reference gathers `edge.view(B,-1)` with PathIndex.path_indices built for default_size (H,W)
+    and max-pools each path; here the radius is all that is needed (`path_index.radius`, or `radius=`)."""
+    _lib.require_cuda(edge)
+    if radius is None:
+        if path_index is None:
+            raise ValueError("to_affinity needs a PathIndex or a radius")
+        radius = int(path_index.radius)
+    if edge.dim() == 4:
+        if edge.shape[1] != 1:
+            raise ValueError("to_affinity expects one edge channel, got %s" % (tuple(edge.shape),))
+        edge = edge[:, 0]
+    if edge.dim() != 3:
+        raise ValueError("to_affinity expects [B,1,H,W] or [B,H,W], got %s" % (tuple(edge.shape),))
+    return _ToAffinity.apply(edge, int(radius))
+
+
 def random_walk_batch(x, edge, chan_offsets, radius=5, beta=10, n_iter=256, variant=0):
     """Batched walk through the C ABI.  x cuda fp32 [total_channels,h,w]; edge cuda fp32
     [n_img,h,w]; chan_offsets: int sequence [n_img+1].  Returns fp32 [total_channels,h,w]."""

@@ -11,6 +11,7 @@ Batched mode keeps the reference's observable behaviour: same files, same names,
 files appear changes (images are bucketed by size, a bucket is flushed when it holds --step_batch images or at the end),
 and file writes overlap the GPU work of the next batch on a small thread pool.
 """
+import contextlib
 import importlib
 import os
 import threading
@@ -39,6 +40,53 @@ def collate_one(batch):
         out["jpeg"] = torch.from_numpy(jpeg)        # variable-length byte stream: no batch dimension
     out["size"] = (int(batch[0]["size"][0]), int(batch[0]["size"][1]))
     return out
+
+
+LOADER_CHUNK = 8
+
+
+def collate_chunk(batch):
+    """Several consecutive items as ONE message from a loader worker: the decoded images (or JPEG byte streams) in one flat uint8
+    tensor, the stored CAMs in one flat fp32 tensor.  A DataLoader hands every tensor of every item to the main process through its
+    own file-descriptor exchange (~0.5 ms each): with batch_size=1 and five tensors per item that alone capped the label steps at
+    ~400 images/s on the B200 host, whatever the number of workers (profiles/r02_config4_loader.md).  `split_chunk` turns the
+    message back into batch_size=1 packs (views, no copies)."""
+    out = {"names": [b["name"] for b in batch], "sizes": [(int(b["size"][0]), int(b["size"][1])) for b in batch],
+           "label": torch.stack([torch.as_tensor(b["label"]) for b in batch])}
+    kinds, shapes, parts = [], [], []
+    for b in batch:
+        k = "jpeg" if "jpeg" in b else "img_u8"
+        a = np.ascontiguousarray(b[k])
+        kinds.append(k)
+        shapes.append(tuple(a.shape))
+        parts.append(a.reshape(-1))
+    out["kinds"], out["shapes"] = kinds, shapes
+    out["blob"] = torch.from_numpy(np.concatenate(parts))
+    if "cam" in batch[0]:
+        out["cam_shapes"] = [tuple(b["cam"].shape) for b in batch]
+        out["cam_blob"] = torch.cat([b["cam"].reshape(-1) for b in batch])
+        out["cam_keys"] = torch.cat([b["cam_keys"].reshape(-1) for b in batch])
+    return out
+
+
+def split_chunk(chunk):
+    """The packs `collate_one` would have produced for the items of a `collate_chunk` message, in order."""
+    o = co = ko = 0
+    for i, name in enumerate(chunk["names"]):
+        shape = chunk["shapes"][i]
+        n = int(np.prod(shape))
+        pack = {"name": [name], "size": chunk["sizes"][i], "label": chunk["label"][i:i + 1]}
+        view = chunk["blob"][o:o + n]
+        pack[chunk["kinds"][i]] = view if chunk["kinds"][i] == "jpeg" else view.view((1,) + shape)
+        o += n
+        if "cam_blob" in chunk:
+            cs = chunk["cam_shapes"][i]
+            cn = int(np.prod(cs))
+            pack["cam"] = chunk["cam_blob"][co:co + cn].view((1,) + cs)
+            pack["cam_keys"] = chunk["cam_keys"][ko:ko + cs[0]].view(1, -1)
+            co += cn
+            ko += cs[0]
+        yield pack
 
 
 def progress(process_id, n_gpus, it, n_items):
@@ -204,6 +252,20 @@ class StepContext:
         self.writer = Writer(device)
         self._pinned = {}
         self._jpeg = None
+        self.phase_seconds = {} if os.environ.get("IRN_STEP_PROFILE") else None     # host time per phase of the batch bodies
+
+    @contextlib.contextmanager
+    def phase(self, name):
+        """Host-side stopwatch around a phase of a batch body (IRN_STEP_PROFILE only; GPU work is asynchronous, so this is the
+        time the main thread spent issuing it or waiting on something)."""
+        if self.phase_seconds is None:
+            yield
+            return
+        t = time.perf_counter()
+        try:
+            yield
+        finally:
+            self.phase_seconds[name] = self.phase_seconds.get(name, 0.0) + time.perf_counter() - t
 
     def stack_images(self, packs):
         """The decoded images of a bucket as one device uint8 [N,H,W,3], staged through pinned host memory (two alternating
@@ -261,33 +323,43 @@ def work_loop(process_id, model, dataset, args, per_image, per_batch=None):
     (step/make_cam.py:16-59), with the per-image / per-batch body supplied by the step."""
     shard = dataset[process_id]
     n_gpus = max(torch.cuda.device_count(), 1)
-    loader = DataLoader(shard, shuffle=False, num_workers=args.num_workers // n_gpus, pin_memory=False, collate_fn=collate_one)
     scales = getattr(getattr(shard, "dataset", shard), "scales", (1.0,))
     bsz = step_batch(args)
+    workers = args.num_workers // n_gpus
+    batched = not (per_batch is None or bsz == 1 or not device_pyramid(args))
+    if batched:     # items travel in chunks (collate_chunk); the workers keep about two buckets' worth of them in flight
+        depth = {"prefetch_factor": max(2, -(-2 * bsz // (workers * LOADER_CHUNK)))} if workers > 0 else {}
+        loader = DataLoader(shard, shuffle=False, batch_size=LOADER_CHUNK, num_workers=workers, pin_memory=False, collate_fn=collate_chunk, **depth)
+    else:
+        loader = DataLoader(shard, shuffle=False, num_workers=workers, pin_memory=False, collate_fn=collate_one)
     with torch.no_grad(), torch.cuda.device(process_id):
         model.cuda()
-        if per_batch is None or bsz == 1 or not device_pyramid(args):
+        if not batched:
             for it, pack in enumerate(loader):
                 per_image(model, attach_pyramid(pack, scales), args)
                 progress(process_id, n_gpus, it, len(shard))
             return
         ctx = StepContext(model, args, torch.device("cuda", process_id), scales)
+        chunked = True
         if getattr(args, "loader_threads", False):     # measured slower than forked workers (GIL: 82 vs 148 images/s, bench --config 4): off
-            loader = threaded_loader(shard, max(2, args.num_workers // n_gpus), prefetch=2 * bsz)
+            loader, chunked = threaded_loader(shard, max(2, args.num_workers // n_gpus), prefetch=2 * bsz), False
         buckets = {}
         prof = os.environ.get("IRN_STEP_PROFILE")          # host-side time split of the loop (development aid), printed to stderr
         t_load = t_body = 0.0
         t_start = t_prev = time.perf_counter()
         try:
-            for it, pack in enumerate(loader):
+            it = 0
+            for msg in loader:
                 t_now = time.perf_counter()
                 t_load += t_now - t_prev
-                key = (pack["size"], "jpeg" if "jpeg" in pack else tuple(pack["img_u8"].shape))
-                b = buckets.setdefault(key, [])
-                b.append(pack)
-                if len(b) >= bsz:
-                    per_batch(ctx, buckets.pop(key))
-                progress(process_id, n_gpus, it, len(shard))
+                for pack in (split_chunk(msg) if chunked else (msg,)):
+                    key = (pack["size"], "jpeg" if "jpeg" in pack else tuple(pack["img_u8"].shape))
+                    b = buckets.setdefault(key, [])
+                    b.append(pack)
+                    if len(b) >= bsz:
+                        per_batch(ctx, buckets.pop(key))
+                    progress(process_id, n_gpus, it, len(shard))
+                    it += 1
                 t_prev = time.perf_counter()
                 t_body += t_prev - t_now
             for packs in buckets.values():
@@ -303,6 +375,8 @@ def work_loop(process_id, model, dataset, args, per_image, per_batch=None):
             print("[irn_b200 step profile] rank %d: %d images, %.2f s total = waiting for the loader %.2f + batch bodies (host) %.2f + "
                   "GPU drain %.2f + file writes drain %.2f" % (process_id, len(shard), t_end - t_start, t_load, t_body, t_sync - t_loop,
                                                                 t_end - t_sync), file=sys.stderr, flush=True)
+            print("[irn_b200 step profile] rank %d: batch-body phases (host seconds): %s" %
+                  (process_id, ", ".join("%s %.2f" % kv for kv in sorted(ctx.phase_seconds.items(), key=lambda kv: -kv[1]))), file=sys.stderr, flush=True)
 
 
 def run_step(args, work, module_name, class_name, weights_path, strict, list_path, scales, opening="[ ", cam_dir=None):
@@ -337,8 +411,12 @@ def to_device_list(ctx, tensors):
     """A list of small host tensors [K_i,h,w] -> list of device views of ONE uploaded buffer (one H2D copy per batch instead of one
     per image)."""
     counts = [int(t.shape[0]) for t in tensors]
-    flat = torch.cat([t.float() for t in tensors], 0) if len(tensors) > 1 else tensors[0].float()
-    dev = flat.to(ctx.device, non_blocking=True)
+    # through PINNED memory (torch's caching host allocator keeps the block alive until the copy has run): a copy from pageable memory
+    # is staged in stream order, i.e. the host would sit here until the GPU has finished everything issued before it -- measured
+    # 1.0 s of a 2.3 s sem-seg pass waiting for the IRNet forward of the same bucket (profiles/r02_config4_loader.md)
+    staged = torch.empty((sum(counts),) + tuple(tensors[0].shape[1:]), dtype=torch.float32, pin_memory=True)
+    torch.cat([torch.as_tensor(t).float() for t in tensors], 0, out=staged)
+    dev = staged.to(ctx.device, non_blocking=True)
     out, o = [], 0
     for c in counts:
         out.append(dev[o:o + c])

@@ -33,11 +33,14 @@ def _save(ctx, names, keys, strided, highres, out_dir):
 def cam_batch(ctx, packs):
     """The same body for a bucket of equally-sized decoded images (irn_b200.pipeline stages C1-C4)."""
     args = ctx.args
-    x = ctx.stack_images(packs)
+    with ctx.phase("stack + upload images"):
+        x = ctx.stack_images(packs)
     labels = torch.cat([p["label"] for p in packs], 0)
-    xs = ctx.pipe.pyramids(x, ctx.scales)
-    keys, strided, highres = ctx.pipe.cam_stage(xs, labels, packs[0]["size"], want_highres=True, scales=ctx.scales)
-    ctx.writer.submit(_save, ctx, [p["name"][0] for p in packs], keys, strided, highres, args.cam_out_dir)
+    with ctx.phase("pyramids + cam forward + merge (issue)"):
+        xs = ctx.pipe.pyramids(x, ctx.scales)
+        keys, strided, highres = ctx.pipe.cam_stage(xs, labels, packs[0]["size"], want_highres=True, scales=ctx.scales)
+    with ctx.phase("hand to writer"):
+        ctx.writer.submit(_save, ctx, [p["name"][0] for p in packs], keys, strided, highres, args.cam_out_dir)
 
 
 def _work(process_id, model, dataset, args):

@@ -32,14 +32,21 @@ def sem_seg_batch(ctx, packs):
     """step/make_sem_seg_labels.py:28-51 for a bucket of equally-sized images: one IRNet forward, one batched walk."""
     args = ctx.args
     names = [voc_data.decode_int_filename(p["name"][0]) for p in packs]
-    keys, cams = _common.load_cam_dicts(ctx, packs, names, args.cam_out_dir)
-    x = ctx.stack_images(packs)
-    x1 = ctx.pipe.pyramids(x, (1.0,))[0]
-    edges, _ = ctx.pipe.irn_stage(x1)
-    seeds = _common.to_device_list(ctx, cams)
-    rw, counts = ctx.pipe.walk_stage(seeds, edges)
-    labels = ctx.pipe.label_stage(rw, counts, keys, packs[0]["size"], float(args.sem_seg_bg_thres))
-    ctx.writer.submit(_save, ctx, names, labels, args.sem_seg_out_dir)
+    with ctx.phase("cam dicts"):
+        keys, cams = _common.load_cam_dicts(ctx, packs, names, args.cam_out_dir)
+    with ctx.phase("stack + upload images"):
+        x = ctx.stack_images(packs)
+    with ctx.phase("irn forward (issue)"):
+        x1 = ctx.pipe.pyramids(x, (1.0,))[0]
+        edges, _ = ctx.pipe.irn_stage(x1)
+    with ctx.phase("upload cams"):
+        seeds = _common.to_device_list(ctx, cams)
+    with ctx.phase("walk (issue)"):
+        rw, counts = ctx.pipe.walk_stage(seeds, edges)
+    with ctx.phase("labels (issue)"):
+        labels = ctx.pipe.label_stage(rw, counts, keys, packs[0]["size"], float(args.sem_seg_bg_thres))
+    with ctx.phase("hand to writer"):
+        ctx.writer.submit(_save, ctx, names, labels, args.sem_seg_out_dir)
 
 
 def _work(process_id, model, dataset, args):

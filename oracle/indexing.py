@@ -92,6 +92,34 @@ def edge_to_affinity(edge_padded, path_indices):
     return np.concatenate(out, axis=0)
 
 
+# --------------------------------------------------------------------------- N4 (training side)
+def to_affinity(edge, path_indices):
+    """AffinityDisplacementLoss.to_affinity (net/resnet50_irn.py:162-175): edge float32 [B, H, W] (un-padded; PathIndex built
+    for default_size (H, W)); per length group gather `edge.view(B,-1)` at the path indices and take 1 - max over the path.
+    Returns (aff float32 [B, n_dst, n_src], arg int64 [B, n_dst, n_src]) where arg is the flat H*W index of the FIRST maximum
+    along the path (np.argmax = max_pool2d's choice): what autograd differentiates through."""
+    B = edge.shape[0]
+    flat = np.asarray(edge, dtype=np.float32).reshape(B, -1)
+    affs, args = [], []
+    for t in path_indices:                     # t: int64 [n_paths, L, n_src]
+        g = flat[:, t]                         # [B, n_paths, L, n_src]
+        at = g.argmax(axis=2)                  # first maximum
+        affs.append(np.float32(1) - np.take_along_axis(g, at[:, :, None, :], axis=2)[:, :, 0, :])
+        args.append(np.take_along_axis(np.broadcast_to(t[None], g.shape), at[:, :, None, :], axis=2)[:, :, 0, :])
+    return np.concatenate(affs, axis=1), np.concatenate(args, axis=1)
+
+
+def to_affinity_backward(grad_aff, arg, hw):
+    """Gradient of `to_affinity` w.r.t. the edge map: aff = 1 - edge[arg]  =>  grad_edge[arg] -= grad_aff (the scatter-add that
+    index_select's backward performs, after max_pool2d's backward has routed each gradient to its maximum).  float64
+    accumulation: the reference's index_add_ order is not defined, the exact sum is the fair target.  Returns float64 [B, hw]."""
+    B = grad_aff.shape[0]
+    out = np.zeros((B, hw), np.float64)
+    for b in range(B):
+        np.add.at(out[b], arg[b].reshape(-1), -grad_aff[b].reshape(-1).astype(np.float64))
+    return out
+
+
 # --------------------------------------------------------------------------- R4
 def affinity_sparse2dense(aff, src, dst, n_vertices):
     """Symmetric dense matrix with unit diagonal (misc/indexing.py:112-129)."""

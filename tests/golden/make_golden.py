@@ -83,6 +83,29 @@ def gen_affinity(ref_indexing):
     print("affinity", aff.shape)
 
 
+def gen_to_affinity(ref_indexing):
+    """The reference's AffinityDisplacementLoss.to_affinity (net/resnet50_irn.py:162-175), forward and autograd backward, called
+    UNBOUND on a stub that carries only what the method reads (the path-index buffers): constructing the real module would build
+    a ResNet-50 for nothing."""
+    from net import resnet50_irn as ref_irn
+    out = {}
+    for tag, r, h, w, B, kind, seed in (("r10", 10, 32, 36, 1, "sigmoid4", 3), ("r5", 5, 24, 31, 3, "uniform", 5), ("r10b", 10, 30, 30, 2, "bimodal", 9)):
+        pi = ref_indexing.PathIndex(r, (h, w))
+        stub = types.SimpleNamespace(n_path_lengths=len(pi.path_indices),
+                                     _buffers={ref_irn.AffinityDisplacementLoss.path_indices_prefix + str(i): torch.from_numpy(p)
+                                               for i, p in enumerate(pi.path_indices)})
+        edge = np.stack([synth.edge_map(h, w, kind, seed + b) for b in range(B)])                # [B,1,h,w] like sigmoid(edge_out)
+        e = torch.from_numpy(edge).requires_grad_(True)
+        aff = ref_irn.AffinityDisplacementLoss.to_affinity(stub, e)
+        g = torch.from_numpy(np.random.RandomState(seed).standard_normal(tuple(aff.shape)).astype(np.float32))
+        aff.backward(g)
+        out[tag + "_edge"], out[tag + "_aff"] = edge, aff.detach().numpy()
+        out[tag + "_grad_edge"] = e.grad.numpy()       # for grad_aff = RandomState(seed).standard_normal(aff.shape) as float32
+        out[tag + "_radius"], out[tag + "_seed"] = r, seed
+        print("to_affinity", tag, tuple(aff.shape), float(np.abs(e.grad.numpy()).max()))
+    np.savez_compressed(os.path.join(HERE, "to_affinity.npz"), **out)
+
+
 def gen_nets():
     import net.resnet50_cam as rcam
     import net.resnet50_irn as rirn
@@ -332,6 +355,8 @@ def main():
         gen_path_index(ref_indexing)
     if want("aff"):
         gen_affinity(ref_indexing)
+    if want("toaff"):
+        gen_to_affinity(ref_indexing)
     if want("rw"):
         for c in RW_CASES:
             gen_rw(ref_indexing, c)

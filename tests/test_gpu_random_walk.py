@@ -32,6 +32,32 @@ def test_edge_to_affinity_exact(cuda_dev):
         assert np.array_equal(indexing.edge_to_affinity(_t(e, cuda_dev), r).cpu().numpy()[0], W)
 
 
+@pytest.mark.parametrize("tag", ["r10", "r5", "r10b"])
+def test_to_affinity_forward_backward_vs_reference(cuda_dev, tag):
+    """N4: indexing.to_affinity (the body for AffinityDisplacementLoss.to_affinity, net/resnet50_irn.py:162-175) against the
+    unmodified reference method: forward bit-exact, gradient (autograd through index_select + max_pool2d in the reference)
+    within fp32 summation order; "r10b" has saturated edges (ties: the first maximum along the path takes the gradient)."""
+    g = np.load(golden_path("to_affinity.npz"))
+    edge, r = g[tag + "_edge"], int(g[tag + "_radius"])
+    e = _t(edge, cuda_dev).requires_grad_(True)
+    aff = indexing.to_affinity(e, radius=r)
+    assert np.array_equal(aff.detach().cpu().numpy(), g[tag + "_aff"])
+    grad_aff = np.random.RandomState(int(g[tag + "_seed"])).standard_normal(tuple(aff.shape)).astype(np.float32)
+    aff.backward(_t(grad_aff, cuda_dev))
+    ref = g[tag + "_grad_edge"]
+    err = float(np.abs(e.grad.cpu().numpy() - ref).max())
+    assert err < 1e-5 * max(1.0, float(np.abs(ref).max())), "grad_edge max-abs err %g" % err
+    # the oracle's exact (fp64) scatter and its argmax agree with the kernel's routing
+    B, _, h, w = edge.shape
+    _, arg = oi.to_affinity(edge[:, 0], oi.PathIndex(r, (h, w)).path_indices)
+    truth = oi.to_affinity_backward(grad_aff, arg, h * w).reshape(B, 1, h, w)
+    assert np.abs(e.grad.cpu().numpy() - truth).max() < 1e-5 * max(1.0, float(np.abs(truth).max()))
+    # through a PathIndex object, no gradient requested (inference): same values, [B,H,W] input accepted
+    pi = indexing.PathIndex(r, (h, w))
+    again = indexing.to_affinity(_t(edge[:, 0], cuda_dev), pi)
+    assert np.array_equal(again.cpu().numpy(), g[tag + "_aff"])
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(golden_path("rw_*.npz"))), ids=os.path.basename)
 @pytest.mark.parametrize("variant", [0, 1, 2, 4])
 def test_random_walk_vs_reference(cuda_dev, path, variant):

@@ -133,3 +133,40 @@ def test_threaded_loader_matches_dataloader_order():
     ref = list(DataLoader(shard, shuffle=False, num_workers=0, collate_fn=_common.collate_one))
     for a, b in zip(got, ref):
         assert a["size"] == b["size"] and torch.equal(a["img_u8"], b["img_u8"]) and torch.equal(a["label"], b["label"])
+
+
+def test_chunked_messages_split_back_into_batch1_packs(tmp_path):
+    """Batched mode ships LOADER_CHUNK items per worker message (step/_common.collate_chunk: one flat tensor for the pixels / JPEG
+    bytes, one for the stored CAMs); split_chunk must give back exactly the packs of the batch-size-1 collation, in order,
+    including ragged items (different image sizes, different K, a JPEG byte stream next to decoded pixels)."""
+    from torch.utils.data import DataLoader
+    cam_dir = tmp_path / "cam"
+    os.makedirs(cam_dir)
+    rng = np.random.RandomState(0)
+    items = []
+    for i, (h, w, k) in enumerate([(24, 32, 1), (24, 32, 3), (16, 20, 2)]):
+        item = {"name": "2007_%06d" % i, "size": (h, w), "label": torch.from_numpy(rng.rand(20).astype(np.float32)),
+                "cam_keys": torch.arange(k, dtype=torch.int64) + i, "cam": torch.from_numpy(rng.rand(k, h // 4, w // 4).astype(np.float32))}
+        if i == 1:
+            item["jpeg"] = rng.randint(0, 255, 777).astype(np.uint8)
+        else:
+            item["img_u8"] = rng.randint(0, 255, (h, w, 3)).astype(np.uint8)
+        items.append(item)
+    packs = list(_common.split_chunk(_common.collate_chunk([dict(it) for it in items])))
+    assert len(packs) == 3
+    for it, p in zip(items, packs):
+        ref = _common.collate_one([dict(it)])
+        assert set(p) == set(ref)
+        assert p["name"] == ref["name"] and p["size"] == ref["size"]
+        for k in ("label", "cam", "cam_keys", "img_u8", "jpeg"):
+            if k in ref:
+                assert p[k].shape == ref[k].shape and p[k].dtype == ref[k].dtype and torch.equal(p[k], ref[k]), k
+    # through a real DataLoader with workers, over a stride shard: same items, same order as the batch-1 loader
+    ds = dl.SyntheticMSF(11, size=(24, 32), scales=(1.0,), decode_only=True)
+    shard = torchutils.split_dataset(ds, 2)[1]
+    got = [p for msg in DataLoader(shard, shuffle=False, batch_size=_common.LOADER_CHUNK // 2, num_workers=2, collate_fn=_common.collate_chunk)
+           for p in _common.split_chunk(msg)]
+    ref = list(DataLoader(shard, shuffle=False, num_workers=0, collate_fn=_common.collate_one))
+    assert [p["name"] for p in got] == [p["name"] for p in ref] == [["2007_%06d" % i] for i in (1, 3, 5, 7, 9)]
+    for a, b in zip(got, ref):
+        assert a["size"] == b["size"] and torch.equal(a["img_u8"], b["img_u8"]) and torch.equal(a["label"], b["label"])

@@ -58,6 +58,22 @@ def test_edge_to_affinity_matches_reference():
     assert np.array_equal(W, win)
 
 
+@pytest.mark.parametrize("tag", ["r10", "r5", "r10b"])
+def test_to_affinity_oracle_matches_reference(tag):
+    """N4: the restated AffinityDisplacementLoss.to_affinity (net/resnet50_irn.py:162-175) against the unmodified method's output
+    and against the gradient autograd computed through its index_select + max_pool2d (tests/golden/make_golden.py:gen_to_affinity)."""
+    g = np.load(golden_path("to_affinity.npz"))
+    edge, r = g[tag + "_edge"][:, 0], int(g[tag + "_radius"])
+    B, h, w = edge.shape
+    pi = oi.PathIndex(r, (h, w))
+    aff, arg = oi.to_affinity(edge, pi.path_indices)
+    assert np.array_equal(aff, g[tag + "_aff"])                       # gather / max / 1-x: exact
+    grad_aff = np.random.RandomState(int(g[tag + "_seed"])).standard_normal(aff.shape).astype(np.float32)
+    ge = oi.to_affinity_backward(grad_aff, arg, h * w).reshape(B, 1, h, w)
+    ref = g[tag + "_grad_edge"]
+    assert np.abs(ge - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())    # fp32 scatter-add in the reference vs the exact sum
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(golden_path("rw_*.npz"))), ids=os.path.basename)
 def test_random_walk_oracle(path):
     g = np.load(path)

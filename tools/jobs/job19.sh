@@ -1,0 +1,9 @@
+set -x
+cd /root/repo
+mkdir -p gpurun_out/j19
+(timeout 600 python -m pytest tests/test_gpu_random_walk.py -m gpu -q -k "affinity" > gpurun_out/j19/pytest_aff.txt 2>&1; echo "rc=$?" >> gpurun_out/j19/pytest_aff.txt); tail -15 gpurun_out/j19/pytest_aff.txt
+IRN_STEP_PROFILE=1 timeout 600 python bench.py --config 4 --steps 1 --warmup 3 --no-cpu-baseline --no-eager-baseline > gpurun_out/j19/c4.json 2> gpurun_out/j19/c4.err; echo rc=$?
+grep "step profile" gpurun_out/j19/*.err | tail -2
+python -c "
+import json
+d=json.load(open('gpurun_out/j19/c4.json')); print(d['value'], d['rank0_pass_seconds'], d['clocks'])"
