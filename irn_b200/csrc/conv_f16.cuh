@@ -192,6 +192,20 @@ __device__ __forceinline__ void f16_epilogue(const TcArgs& args, float* staging,
             for (int i = 0; i < 8; ++i)
                 res[cc * 8 + i] = (res_base && ((okmask >> i) & 1u)) ? __ldg(reinterpret_cast<const float4*>(res_base + off(i) + cc * 32))
                                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        // the NEXT tile's residual slice is asked into L2 now (no registers held): its loads, issued only after this tile's stores,
+        // then pay an L2 hit instead of a DRAM round trip
+        if (res_base && id + (int)gridDim.x < total && !(args.mode & 8)) {
+            int nb, noy0, nox0, nn0;
+            f16_tile_coords(args, n_tiles, BN, id + (int)gridDim.x, nb, noy0, nox0, nn0);
+            const float* nres = args.residual + (((size_t)nb * args.Ho + noy0) * args.Wo + nox0) * args.Cout + nn0 + hf * kCols + c8 * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (noy0 + q * 2 + (i >> 2) < args.Ho && nox0 + (i & 3) * 4 + sub < args.Wo) {
+#pragma unroll
+                    for (int cc = 0; cc < kChunks; ++cc)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nres + off(i) + cc * 32));
+                }
+        }
         mbar_wait(&tmem_full[set], use & 1);
         tc_fence_after();
 #pragma unroll

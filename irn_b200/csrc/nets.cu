@@ -501,7 +501,8 @@ static int launch_tc_ts(const Conv& c, const float* in, int B, int H, int W, int
 // ---- f16x3 kernels (conv_f16.cuh)
 static int f16_mode_flags() {
     static const int spin = getenv("IRN_F16_SPIN") ? atoi(getenv("IRN_F16_SPIN")) : 1;     // 0: suspending try_wait on the critical path (A/B runs)
-    return spin ? 0 : 4;
+    static const int pf = getenv("IRN_F16_RES_PREFETCH") ? atoi(getenv("IRN_F16_RES_PREFETCH")) : 1;   // 0: no L2 prefetch of the next tile's residual (A/B runs)
+    return (spin ? 0 : 4) | (pf ? 0 : 8);
 }
 
 // Second input of a K-concatenated 1x1 conv (Block::c3ds): NHWC [B, H2, W2, cin2] sampled with pixel stride `stride`
