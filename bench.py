@@ -640,7 +640,10 @@ def main():
                         "images_per_launch": n_img, "channels_per_launch": totc, "algorithmic_bytes_per_launch": alg,
                         "algorithmic_bytes_formula": "256 steps x N=16384 x [images x (4*34 + 4) + channels x 2*8] (SURVEY.md 8(d), fp64 state)",
                         "note": "weights stay resident in shared memory for all steps of a launch, so DRAM traffic (`traffic`) is a small "
-                                "fraction of the algorithmic bytes and frac may exceed 1; the kernel's real ceiling is shared-memory bandwidth",
+                                "fraction of the algorithmic bytes and frac may exceed 1; the kernel's real ceiling is shared-memory bandwidth, which scales "
+                                "with the SM clock: the launch is timed INSIDE the step, at the clock the power cap leaves the conv kernels "
+                                "(`clocks.sm_mhz`): 0.80 at ~1830 MHz (round 1's lighter conv path), ~0.70 at ~1570 MHz; it occupies 7 clusters x 16 "
+                                "CTAs = 112 of 148 SMs (one 16-CTA cluster per GPC that has 16 free SMs)",
                         "clusters": clusters, "smem_wavefront_frac": smem_cycles / (launch_ms * 1e-3 * clocks_mhz(clocks) * 1e6)}
         else:
             traffic = None
