@@ -72,3 +72,13 @@ def test_device_entry_points_refuse_cpu_tensors(built_lib):
     from irn_b200 import indexing, _lib
     with pytest.raises(_lib.IrnError):
         indexing.propagate_to_edge(torch.zeros(1, 8, 8), torch.zeros(1, 8, 8))
+
+
+def test_to_affinity_refuses_cpu_tensors_and_bad_arguments(built_lib):
+    """N4's differentiable op has no CPU path either; argument errors are raised before anything is launched."""
+    import torch
+    from irn_b200 import indexing, _lib
+    with pytest.raises(_lib.IrnError):
+        indexing.to_affinity(torch.zeros(1, 1, 12, 24), radius=5)
+    with pytest.raises(_lib.IrnError):
+        indexing.to_affinity(torch.zeros(1, 12, 24), indexing.PathIndex(5, (12, 24)))
