@@ -39,6 +39,18 @@ with torch.no_grad():
                                         radius=5, beta=10, exp_times=et).numpy().astype(np.float32)
 out["rw_name"] = name
 out["rw"] = rw.reshape(-1).tolist()
+# N4: AffinityDisplacementLoss.to_affinity, forward and autograd gradient, case "r5" of make_golden.gen_to_affinity
+import types
+from net import resnet50_irn as ref_irn
+r, h, w, B, kind, seed = 5, 24, 31, 3, "uniform", 5
+pi = ref_indexing.PathIndex(r, (h, w))
+stub = types.SimpleNamespace(n_path_lengths=len(pi.path_indices),
+                             _buffers={ref_irn.AffinityDisplacementLoss.path_indices_prefix + str(i): torch.from_numpy(p) for i, p in enumerate(pi.path_indices)})
+e = torch.from_numpy(np.stack([synth.edge_map(h, w, kind, seed + b) for b in range(B)])).requires_grad_(True)
+aff = ref_irn.AffinityDisplacementLoss.to_affinity(stub, e)
+aff.backward(torch.from_numpy(np.random.RandomState(seed).standard_normal(tuple(aff.shape)).astype(np.float32)))
+out["toaff_sha"] = hashlib.sha256(np.ascontiguousarray(aff.detach().numpy()).tobytes()).hexdigest()
+out["toaff_grad"] = e.grad.numpy().reshape(-1).tolist()
 print("RESULT" + json.dumps(out))
 """
 
@@ -54,6 +66,9 @@ def test_fixtures_are_live_reference_outputs():
     g = np.load(golden_path("affinity_12x17.npz"))
     assert out["aff_sha"] == hashlib.sha256(np.ascontiguousarray(g["aff"]).tobytes()).hexdigest()
     g = np.load(golden_path("rw_%s.npz" % out["rw_name"]))
+    t = np.load(golden_path("to_affinity.npz"))
+    assert out["toaff_sha"] == hashlib.sha256(np.ascontiguousarray(t["r5_aff"]).tobytes()).hexdigest()
+    assert np.abs(np.asarray(out["toaff_grad"], np.float32).reshape(t["r5_grad_edge"].shape) - t["r5_grad_edge"]).max() < 1e-5
     live = np.asarray(out["rw"], np.float32).reshape(g["rw"].shape)
     # same code, same seeds, same machine class: the matrix products may differ in the last bits between BLAS builds / thread counts
     assert np.abs(live - g["rw"]).max() < 1e-6
